@@ -1,0 +1,177 @@
+// Spatial attention over the 17 joints of one (stream, frame), all 8 heads per CTA (one warp per head)
+// (reference: common/mixste.py:63-82 Attention.forward as called from the STEblocks, mixste.py:239-244,264-269).
+//
+// 17x17 score tiles are far too small for tcgen05 (M=128 minimum), so this kernel stays on the warp-level
+// mma.sync.m16n8k16 path with a shuffle softmax: Q (padded to 32 rows) x K^T (padded to 24 keys), softmax in
+// registers, P (32x32) x V (32 keys x 64).  Token order is [S, J, F]: the 17 rows of a spatial sequence are F rows
+// apart, each a contiguous 3 KB fp16 qkv row, so the CTA gathers 17 rows with cp.async and every warp works from smem.
+// It is an HBM-bound kernel (4 KB/token in+out); the MMA shape padding is irrelevant to its speed.
+#pragma once
+#include "ptx.cuh"
+
+namespace d3dp {
+
+struct AttnSParams {
+  const __half* qkv;  // [T, 1536]
+  __half* out;        // [T, 512]
+  int num_streams;    // S
+  int F;
+  float scale;        // head_dim^-0.5
+};
+
+constexpr int SP_J = 17;
+constexpr int SP_ROW_HALFS = 1536 + 8;  // +16 B pad: consecutive joints land 4 banks apart -> conflict-free fragments
+constexpr int SP_SMEM_BYTES = SP_J * SP_ROW_HALFS * 2;
+
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256) attn_spatial_kernel(const AttnSParams p) {
+  extern __shared__ __align__(16) uint8_t sp_smem[];
+  __half* sm = reinterpret_cast<__half*>(sp_smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int num_items = p.num_streams * p.F;
+
+  for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    const int s = item / p.F, f = item % p.F;
+    // gather the 17 qkv rows of this (stream, frame): row(j) = (s*17 + j)*F + f
+    __syncthreads();  // previous item fully consumed
+    for (int idx = threadIdx.x; idx < SP_J * 192; idx += blockDim.x) {
+      const int j = idx / 192, ch = idx % 192;  // 192 x 16 B per row
+      const __half* src = p.qkv + (static_cast<size_t>(s * SP_J + j) * p.F + f) * 1536 + ch * 8;
+      const uint32_t dst = smem_u32(sm + j * SP_ROW_HALFS + ch * 8);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    const int h = warp;
+    const __half* Q = sm + h * 64;
+    const __half* K = sm + 512 + h * 64;
+    const __half* V = sm + 1024 + h * 64;
+    auto ld32 = [&](const __half* base, int row, int col) -> uint32_t {
+      return row < SP_J ? *reinterpret_cast<const uint32_t*>(base + row * SP_ROW_HALFS + col) : 0u;
+    };
+
+    // ---- S = Q K^T : 2 m-tiles (rows 0-15, 16-31) x 3 n-tiles (keys 0-7, 8-15, 16-23), k = 64 in 4 steps
+    float sacc[2][3][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sacc[mt][nt][i] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int k0 = ks * 16 + 2 * t;
+      uint32_t a[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        a[mt][0] = ld32(Q, mt * 16 + g, k0);
+        a[mt][1] = ld32(Q, mt * 16 + g + 8, k0);
+        a[mt][2] = ld32(Q, mt * 16 + g, k0 + 8);
+        a[mt][3] = ld32(Q, mt * 16 + g + 8, k0 + 8);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        const uint32_t b0 = ld32(K, nt * 8 + g, k0);
+        const uint32_t b1 = ld32(K, nt * 8 + g, k0 + 8);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) mma_16816(sacc[mt][nt], a[mt], b0, b1);
+      }
+    }
+    // ---- softmax over the 17 valid keys; C fragment: c0,c1 -> (row g, keys nt*8+2t, +1); c2,c3 -> row g+8
+    uint32_t pa[2][2][4];  // P as A fragments: [m-tile][k-step of 16 keys]
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int key = nt * 8 + 2 * t + (i & 1);
+          if (key < SP_J) mx[i >> 1] = fmaxf(mx[i >> 1], sacc[mt][nt][i]);
+        }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
+        mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
+      }
+      float sum[2] = {0.f, 0.f};
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int key = nt * 8 + 2 * t + (i & 1);
+          const float e = key < SP_J ? __expf((sacc[mt][nt][i] - mx[i >> 1]) * p.scale) : 0.f;
+          sacc[mt][nt][i] = e;
+          sum[i >> 1] += e;
+        }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        sum[hh] += __shfl_xor_sync(0xffffffffu, sum[hh], 1);
+        sum[hh] += __shfl_xor_sync(0xffffffffu, sum[hh], 2);
+        sum[hh] = 1.0f / sum[hh];
+      }
+      // normalised probabilities -> fp16 A fragments (k-step 0: keys 0-15 = n-tiles 0,1 ; k-step 1: keys 16-31)
+      pa[mt][0][0] = pack_half2(sacc[mt][0][0] * sum[0], sacc[mt][0][1] * sum[0]);
+      pa[mt][0][1] = pack_half2(sacc[mt][0][2] * sum[1], sacc[mt][0][3] * sum[1]);
+      pa[mt][0][2] = pack_half2(sacc[mt][1][0] * sum[0], sacc[mt][1][1] * sum[0]);
+      pa[mt][0][3] = pack_half2(sacc[mt][1][2] * sum[1], sacc[mt][1][3] * sum[1]);
+      pa[mt][1][0] = pack_half2(sacc[mt][2][0] * sum[0], sacc[mt][2][1] * sum[0]);
+      pa[mt][1][1] = pack_half2(sacc[mt][2][2] * sum[1], sacc[mt][2][3] * sum[1]);
+      pa[mt][1][2] = 0u;
+      pa[mt][1][3] = 0u;
+    }
+    // ---- O = P V : B fragment b0 = {V[k0+2t][n], V[k0+2t+1][n]}, b1 = same at k0+8 ; n = nt*8 + g
+    float oacc[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) oacc[mt][nt][i] = 0.f;
+    auto ldv = [&](int key, int col) -> uint32_t {  // two keys (key, key+1) of one column packed lo/hi
+      const uint16_t lo = key < SP_J ? *reinterpret_cast<const uint16_t*>(V + key * SP_ROW_HALFS + col) : 0;
+      const uint16_t hi = key + 1 < SP_J ? *reinterpret_cast<const uint16_t*>(V + (key + 1) * SP_ROW_HALFS + col) : 0;
+      return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+    };
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int col = nt * 8 + g;
+      {  // k-step 0: keys 0..15
+        const uint32_t b0 = ldv(2 * t, col), b1 = ldv(2 * t + 8, col);
+        mma_16816(oacc[0][nt], pa[0][0], b0, b1);
+        mma_16816(oacc[1][nt], pa[1][0], b0, b1);
+      }
+      {  // k-step 1: keys 16..31 (only key 16 is real)
+        const uint32_t b0 = ldv(16 + 2 * t, col);
+        mma_16816(oacc[0][nt], pa[0][1], b0, 0u);
+        mma_16816(oacc[1][nt], pa[1][1], b0, 0u);
+      }
+    }
+    // ---- store: row g / g+8 of m-tile 0 (joints 0-15), row g of m-tile 1 only for joint 16
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int col = h * 64 + nt * 8 + 2 * t;
+      {
+        const size_t r0 = (static_cast<size_t>(s * SP_J + g) * p.F + f) * 512;
+        const size_t r1 = (static_cast<size_t>(s * SP_J + g + 8) * p.F + f) * 512;
+        *reinterpret_cast<uint32_t*>(p.out + r0 + col) = pack_half2(oacc[0][nt][0], oacc[0][nt][1]);
+        *reinterpret_cast<uint32_t*>(p.out + r1 + col) = pack_half2(oacc[0][nt][2], oacc[0][nt][3]);
+      }
+      if (g == 0) {
+        const size_t r2 = (static_cast<size_t>(s * SP_J + 16) * p.F + f) * 512;
+        *reinterpret_cast<uint32_t*>(p.out + r2 + col) = pack_half2(oacc[1][nt][0], oacc[1][nt][1]);
+      }
+    }
+  }
+}
+
+}  // namespace d3dp

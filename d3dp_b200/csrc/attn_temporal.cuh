@@ -1,0 +1,206 @@
+// Temporal attention over the F frames of one (stream, joint) sequence, one head per work item
+// (reference: common/mixste.py:63-82 Attention.forward as called from the TTEblocks, mixste.py:247-258,270-273).
+//
+// Token order is [S, J, F] so a temporal sequence is F consecutive rows of the fused QKV activation
+// [T, 1536] fp16 (q | k | v thirds, head h = columns 64h..64h+63 of each third, mixste.py:65-67).
+// Per work item (sequence, head): TMA loads Q, K, V [ROWS x 64] (ROWS = F rounded up to 16, <= 256) as three
+// 128-byte-swizzled tiles; S = Q.K^T goes to TMEM with tcgen05 (M=128 per query tile, N=ROWS, K=64); the softmax
+// warpgroup owns one TMEM lane (= query row) per thread: max, exp2, row sum, P -> fp16 written back over S in TMEM;
+// O = P.V is a TS-form tcgen05.mma (A = P from TMEM, B = V from smem, MN-major); O / rowsum is stored as fp16.
+// F <= 256 so one N tile holds the whole row: no online-softmax rescaling.
+#pragma once
+#include "ptx.cuh"
+
+namespace d3dp {
+
+struct AttnTParams {
+  int num_seq;   // S * J
+  int F;         // frames per sequence
+  int rows;      // F rounded up to a multiple of 16 (TMA box rows, UMMA N for S, K extent for P.V)
+  __half* out;   // [T, 512] fp16
+  float scale_log2e;  // head_dim^-0.5 * log2(e)
+};
+
+constexpr int ATT_TILE_BYTES = 256 * 128;          // room for 256 rows x 64 fp16
+constexpr int ATT_STAGE_BYTES = 3 * ATT_TILE_BYTES;  // Q, K, V
+constexpr int ATT_STAGES = 2;
+constexpr int ATT_SMEM_BYTES = ATT_STAGES * ATT_STAGE_BYTES + 256 + 1024;
+
+// barriers: full[2], empty[2], s_full[2], p_full[2], o_full[2], s_free[2]
+__global__ void __launch_bounds__(320, 1)
+attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + ATT_STAGES * ATT_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + 2;
+  uint64_t* sfull_bar = empty_bar + 2;
+  uint64_t* pfull_bar = sfull_bar + 2;
+  uint64_t* ofull_bar = pfull_bar + 2;
+  uint64_t* sfree_bar = ofull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sfree_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_items = p.num_seq * 8;
+  const int n_mtiles = (p.F + 127) / 128;  // 1 or 2 query tiles
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQKV);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+      mbar_init(&sfull_bar[i], 1);
+      mbar_init(&pfull_bar[i], 4);
+      mbar_init(&ofull_bar[i], 1);
+      mbar_init(&sfree_bar[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t bytes = 3u * p.rows * 128u;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int seq = item >> 3, head = item & 7;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = smem + s * ATT_STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], bytes);
+        const int row0 = seq * p.F;
+        tma_load_2d(st, &tmQKV, &full_bar[s], head * 64, row0);
+        tma_load_2d(st + ATT_TILE_BYTES, &tmQKV, &full_bar[s], 512 + head * 64, row0);
+        tma_load_2d(st + 2 * ATT_TILE_BYTES, &tmQKV, &full_bar[s], 1024 + head * 64, row0);
+        if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(128, p.rows, 0, 0);  // S = Q.K^T : both K-major
+      const uint32_t idesc_o = make_idesc_f16(128, 64, 0, 1);      // O = P.V   : A from TMEM, B (V) MN-major
+      const int pv_ksteps = p.rows / 16;
+      int s = 0;
+      uint32_t ph = 0, iph = 0;  // iph: per-item phase of the s/p/o barriers
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t q_base = smem_u32(smem + s * ATT_STAGE_BYTES);
+        const uint32_t k_base = q_base + ATT_TILE_BYTES;
+        const uint32_t v_base = q_base + 2 * ATT_TILE_BYTES;
+        for (int mt = 0; mt < n_mtiles; ++mt) {
+          mbar_wait(&sfree_bar[mt], iph ^ 1);  // previous item's O of this region has been read out
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + mt * 256;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adesc = make_sdesc_sw128(q_base + mt * 128 * 128 + k * 32, 16, 1024);
+            const uint64_t bdesc = make_sdesc_sw128(k_base + k * 32, 16, 1024);
+            mma_f16_ss(d_tmem, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
+          }
+          tc_commit(&sfull_bar[mt]);
+        }
+        for (int mt = 0; mt < n_mtiles; ++mt) {
+          mbar_wait(&pfull_bar[mt], iph);
+          tc_fence_after();
+          const uint32_t p_tmem = tmem_base + mt * 256;        // P: fp16 pairs, columns [0,128)
+          const uint32_t o_tmem = tmem_base + mt * 256 + 128;  // O: fp32, columns [128,192)
+          for (int k = 0; k < pv_ksteps; ++k) {
+            const uint64_t bdesc = make_sdesc_sw128(v_base + k * 16 * 128, 1024, 1024);
+            mma_f16_ts(o_tmem, p_tmem + k * 8, bdesc, idesc_o, k != 0 ? 1u : 0u);
+          }
+          tc_commit(&ofull_bar[mt]);
+        }
+        tc_commit(&empty_bar[s]);  // all MMAs that read this smem stage are done
+        if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
+        iph ^= 1;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax / output warpgroups
+    const int mt = (warp - 2) >> 2;  // query tile owned by this warpgroup
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;  // row within the tile == TMEM lane
+    if (mt < n_mtiles) {
+      const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + mt * 256;
+      const int nchunks = (p.rows + 31) / 32;
+      uint32_t iph = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int seq = item >> 3, head = item & 7;
+        const int qrow = mt * 128 + r;
+        mbar_wait(&sfull_bar[mt], iph);
+        tc_fence_after();
+        // pass 1: row max over the valid keys
+        float mx = -INFINITY;
+        for (int c = 0; c < nchunks; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_s + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < p.F) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+        const float moff = mx * p.scale_log2e;
+        // pass 2: p = exp2(s*c - max*c), row sum, fp16 P written over the consumed part of S
+        float sum = 0.f;
+        for (int c = 0; c < nchunks; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_s + c * 32, v);
+          tmem_ld_wait();
+          uint32_t o[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int k0 = c * 32 + 2 * i;
+            float a = k0 < p.F ? exp2f(__uint_as_float(v[2 * i]) * p.scale_log2e - moff) : 0.f;
+            float b = k0 + 1 < p.F ? exp2f(__uint_as_float(v[2 * i + 1]) * p.scale_log2e - moff) : 0.f;
+            sum += a + b;
+            o[i] = pack_half2(a, b);
+          }
+          tmem_st16(t_s + c * 16, o);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pfull_bar[mt]);
+        // O = P.V done -> normalise and store
+        mbar_wait(&ofull_bar[mt], iph);
+        tc_fence_after();
+        const float inv = 1.0f / sum;
+        __half* orow = p.out + (static_cast<size_t>(seq) * p.F + qrow) * 512 + head * 64;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_s + 128 + c * 32, v);
+          tmem_ld_wait();
+          if (qrow < p.F) {
+            uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              dst[i] = make_uint4(pack_half2(__uint_as_float(v[8 * i]) * inv, __uint_as_float(v[8 * i + 1]) * inv),
+                                  pack_half2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv),
+                                  pack_half2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv),
+                                  pack_half2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sfree_bar[mt]);
+        iph ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace d3dp

@@ -1,0 +1,694 @@
+// C-ABI implementation (include/d3dp_b200.h): handle, weight packing, the denoiser launch sequence, the DDIM
+// sampler loop and the JPMA / q_sample / Philox entry points.  Host code only orchestrates; all arithmetic on the
+// hot path is in the sm_100a kernels of this directory.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/d3dp_b200.h"
+#include "attn_spatial.cuh"
+#include "attn_temporal.cuh"
+#include "elementwise.cuh"
+#include "gemm_tcgen05.cuh"
+
+using namespace d3dp;
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Slot {
+  void* dev = nullptr;
+  int64_t numel = 0;
+  bool f16 = false;
+  bool set = false;
+  int rows = 0, cols = 0;  // GEMM weights: [rows=N, cols=K]
+  CUtensorMap tmap;        // GEMM weights only
+};
+
+struct BlockW {
+  Slot *n1w, *n1b, *qkvw, *qkvb, *projw, *projb, *n2w, *n2b, *fc1w, *fc1b, *fc2w, *fc2b;
+};
+
+}  // namespace
+
+struct d3dp_handle {
+  d3dp_config cfg;
+  int device = 0;
+  int num_sms = 148;
+  std::string err;
+  std::map<std::string, Slot> slots;
+  std::vector<BlockW> sblk, tblk;
+  EncodeTiledFn encode = nullptr;
+  std::vector<double> ac, sqrt_recip, sqrt_recipm1, sqrt_ac, sqrt_1mac;
+  double* d_sqrt_ac = nullptr;   // device copies for q_sample
+  double* d_sqrt_1mac = nullptr;
+  bool attrs_set = false;
+};
+
+namespace {
+
+#define CK(call)                                                                                 \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess) {                                                                     \
+      h->err = std::string(#call) + " failed: " + cudaGetErrorString(e_);                        \
+      return D3DP_E_CUDA;                                                                        \
+    }                                                                                            \
+  } while (0)
+
+int fail(d3dp_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// 2-D fp16 row-major tensor map, 128-byte swizzle, box = {64 columns, box_rows}
+int make_tmap(d3dp_handle* h, CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    h->err = "cuTensorMapEncodeTiled failed (" + std::to_string(static_cast<int>(r)) + ")";
+    return D3DP_E_CUDA;
+  }
+  return D3DP_OK;
+}
+
+void add_slot(d3dp_handle* h, const std::string& name, int64_t numel, bool f16 = false, int rows = 0, int cols = 0) {
+  Slot s;
+  s.numel = numel;
+  s.f16 = f16;
+  s.rows = rows;
+  s.cols = cols;
+  h->slots[name] = s;
+}
+
+void add_block(d3dp_handle* h, const std::string& pre, std::vector<BlockW>& out) {
+  const int C = 512, Hd = 1024;
+  add_slot(h, pre + "norm1.weight", C);
+  add_slot(h, pre + "norm1.bias", C);
+  add_slot(h, pre + "attn.qkv.weight", 3 * C * C, true, 3 * C, C);
+  add_slot(h, pre + "attn.qkv.bias", 3 * C);
+  add_slot(h, pre + "attn.proj.weight", C * C, true, C, C);
+  add_slot(h, pre + "attn.proj.bias", C);
+  add_slot(h, pre + "norm2.weight", C);
+  add_slot(h, pre + "norm2.bias", C);
+  add_slot(h, pre + "mlp.fc1.weight", Hd * C, true, Hd, C);
+  add_slot(h, pre + "mlp.fc1.bias", Hd);
+  add_slot(h, pre + "mlp.fc2.weight", C * Hd, true, C, Hd);
+  add_slot(h, pre + "mlp.fc2.bias", C);
+  out.push_back(BlockW{});
+}
+
+void bind_block(d3dp_handle* h, const std::string& pre, BlockW& b) {
+  auto S = [&](const char* n) { return &h->slots[pre + n]; };
+  b.n1w = S("norm1.weight");   b.n1b = S("norm1.bias");
+  b.qkvw = S("attn.qkv.weight"); b.qkvb = S("attn.qkv.bias");
+  b.projw = S("attn.proj.weight"); b.projb = S("attn.proj.bias");
+  b.n2w = S("norm2.weight");   b.n2b = S("norm2.bias");
+  b.fc1w = S("mlp.fc1.weight"); b.fc1b = S("mlp.fc1.bias");
+  b.fc2w = S("mlp.fc2.weight"); b.fc2b = S("mlp.fc2.bias");
+}
+
+const float* F32(d3dp_handle* h, const char* name) { return static_cast<const float*>(h->slots[name].dev); }
+
+// cosine schedule in float64 (reference: common/diffusionpose.py:42-52,75-78,95-103)
+void compute_schedule(d3dp_handle* h) {
+  const int T = h->cfg.num_timesteps;
+  const double s = 0.008;
+  const double pi = 3.14159265358979323846;
+  std::vector<double> acp(T + 1);
+  for (int i = 0; i <= T; ++i) {
+    const double x = static_cast<double>(i);
+    const double c = std::cos(((x / T) + s) / (1 + s) * pi * 0.5);
+    acp[i] = c * c;
+  }
+  const double a0 = acp[0];
+  for (int i = 0; i <= T; ++i) acp[i] = acp[i] / a0;
+  h->ac.resize(T);
+  h->sqrt_recip.resize(T);
+  h->sqrt_recipm1.resize(T);
+  h->sqrt_ac.resize(T);
+  h->sqrt_1mac.resize(T);
+  double cum = 1.0;
+  for (int t = 0; t < T; ++t) {
+    double beta = 1.0 - (acp[t + 1] / acp[t]);
+    beta = std::fmin(std::fmax(beta, 0.0), 0.999);
+    cum *= (1.0 - beta);
+    h->ac[t] = cum;
+    h->sqrt_recip[t] = std::sqrt(1.0 / cum);
+    h->sqrt_recipm1[t] = std::sqrt(1.0 / cum - 1.0);
+    h->sqrt_ac[t] = std::sqrt(cum);
+    h->sqrt_1mac[t] = std::sqrt(1.0 - cum);
+  }
+}
+
+int upload_schedule(d3dp_handle* h) {
+  const size_t n = h->ac.size() * sizeof(double);
+  if (!h->d_sqrt_ac) CK(cudaMalloc(&h->d_sqrt_ac, n));
+  if (!h->d_sqrt_1mac) CK(cudaMalloc(&h->d_sqrt_1mac, n));
+  CK(cudaMemcpy(h->d_sqrt_ac, h->sqrt_ac.data(), n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_sqrt_1mac, h->sqrt_1mac.data(), n, cudaMemcpyHostToDevice));
+  return D3DP_OK;
+}
+
+template <typename KernelT>
+int set_smem_attr(d3dp_handle* h, KernelT k, int bytes) {
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return D3DP_OK;
+}
+
+// kernel instantiations used by the pipeline
+constexpr int kStagesN256 = 4, kStagesN512 = 2;
+auto* const k_gemm_qkv = gemm_tcgen05_kernel<256, EPI_BIAS_F16, kStagesN256, 4>;
+auto* const k_gemm_fc1 = gemm_tcgen05_kernel<256, EPI_BIAS_GELU_F16, kStagesN256, 8>;
+auto* const k_gemm_proj = gemm_tcgen05_kernel<512, EPI_RES_LN, kStagesN512, 8>;
+auto* const k_gemm_fc2 = gemm_tcgen05_kernel<512, EPI_RES_LN2, kStagesN512, 8>;
+constexpr int kSmemN256 = GemmSmem<256, kStagesN256>::TOTAL;
+constexpr int kSmemN512 = GemmSmem<512, kStagesN512>::TOTAL;
+
+int ensure_attrs(d3dp_handle* h) {
+  if (h->attrs_set) return D3DP_OK;
+  int rc;
+  if ((rc = set_smem_attr(h, k_gemm_qkv, kSmemN256))) return rc;
+  if ((rc = set_smem_attr(h, k_gemm_fc1, kSmemN256))) return rc;
+  if ((rc = set_smem_attr(h, k_gemm_proj, kSmemN512))) return rc;
+  if ((rc = set_smem_attr(h, k_gemm_fc2, kSmemN512))) return rc;
+  if ((rc = set_smem_attr(h, attn_temporal_kernel, ATT_SMEM_BYTES))) return rc;
+  if ((rc = set_smem_attr(h, attn_spatial_kernel, SP_SMEM_BYTES))) return rc;
+  h->attrs_set = true;
+  return D3DP_OK;
+}
+
+int launch_gemm(d3dp_handle* h, int mode, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                cudaStream_t st) {
+  const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int bn = (mode == EPI_BIAS_F16 || mode == EPI_BIAS_GELU_F16) ? 256 : 512;
+  if (p.N % bn != 0 || p.K % GEMM_BK != 0 || p.M <= 0) return fail(h, D3DP_E_INVALID, "gemm: unsupported shape");
+  const int tiles = tiles_m * (p.N / bn);
+  const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+  switch (mode) {
+    case EPI_BIAS_F16: k_gemm_qkv<<<grid, 64 + 4 * 32, kSmemN256, st>>>(tmA, tmB, p); break;
+    case EPI_BIAS_GELU_F16: k_gemm_fc1<<<grid, 64 + 8 * 32, kSmemN256, st>>>(tmA, tmB, p); break;
+    case EPI_RES_LN: k_gemm_proj<<<grid, 64 + 8 * 32, kSmemN512, st>>>(tmA, tmB, p); break;
+    case EPI_RES_LN2: k_gemm_fc2<<<grid, 64 + 8 * 32, kSmemN512, st>>>(tmA, tmB, p); break;
+    default: return fail(h, D3DP_E_INVALID, "gemm: bad mode");
+  }
+  CK(cudaGetLastError());
+  return D3DP_OK;
+}
+
+int launch_attn_temporal(d3dp_handle* h, const __half* qkv, __half* o16, int n_streams, cudaStream_t st) {
+  const int F = h->cfg.frames;
+  if (F > 256) return fail(h, D3DP_E_INVALID, "temporal attention: frames > 256 not supported in this build");
+  const long long T = static_cast<long long>(n_streams) * kJ * F;
+  AttnTParams p;
+  p.num_seq = n_streams * kJ;
+  p.F = F;
+  p.rows = (F + 15) / 16 * 16;
+  p.out = o16;
+  p.scale_log2e = 0.125f * 1.4426950408889634f;
+  CUtensorMap tm;
+  int rc = make_tmap(h, &tm, qkv, static_cast<uint64_t>(T), 1536, static_cast<uint32_t>(p.rows));
+  if (rc) return rc;
+  const int items = p.num_seq * 8;
+  const int grid = items < h->num_sms ? items : h->num_sms;
+  attn_temporal_kernel<<<grid, 320, ATT_SMEM_BYTES, st>>>(tm, p);
+  CK(cudaGetLastError());
+  return D3DP_OK;
+}
+
+int launch_attn_spatial(d3dp_handle* h, const __half* qkv, __half* o16, int n_streams, cudaStream_t st) {
+  AttnSParams p;
+  p.qkv = qkv;
+  p.out = o16;
+  p.num_streams = n_streams;
+  p.F = h->cfg.frames;
+  p.scale = 0.125f;
+  const int items = n_streams * p.F;
+  const int cap = h->num_sms * 2;
+  const int grid = items < cap ? items : cap;
+  attn_spatial_kernel<<<grid, 256, SP_SMEM_BYTES, st>>>(p);
+  CK(cudaGetLastError());
+  return D3DP_OK;
+}
+
+struct Workspace {
+  float* x;
+  __half* a16;
+  __half* qkv16;  // also the fc1 hidden [T,1024] (qkv is dead by then)
+  __half* o16;
+  float* den;     // [n_streams, F, 17, 3]
+  float* tau;     // [B, 512]
+  float* img;     // [B,H,F,17,3]
+  long long* t;   // [B]
+  size_t bytes;
+};
+
+Workspace carve(const d3dp_handle* h, void* base, int B, int H, int n_streams) {
+  const size_t T = static_cast<size_t>(n_streams) * kJ * h->cfg.frames;
+  uint8_t* p = static_cast<uint8_t*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    uint8_t* r = p ? p + off : nullptr;
+    off += align_up(bytes, 1024);
+    return r;
+  };
+  Workspace w;
+  w.x = reinterpret_cast<float*>(take(T * 512 * 4));
+  w.a16 = reinterpret_cast<__half*>(take(T * 512 * 2));
+  w.qkv16 = reinterpret_cast<__half*>(take(T * 1536 * 2));
+  w.o16 = reinterpret_cast<__half*>(take(T * 512 * 2));
+  w.den = reinterpret_cast<float*>(take(static_cast<size_t>(n_streams) * h->cfg.frames * kJ * 3 * 4));
+  w.tau = reinterpret_cast<float*>(take(static_cast<size_t>(B) * 512 * 4));
+  w.img = reinterpret_cast<float*>(take(static_cast<size_t>(B) * H * h->cfg.frames * kJ * 3 * 4));
+  w.t = reinterpret_cast<long long*>(take(static_cast<size_t>(B) * 8));
+  w.bytes = off;
+  return w;
+}
+
+__global__ void fill_t_kernel(long long* t, int B, long long v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) t[i] = v;
+}
+
+// One MixSTE2 forward over n_streams streams (reference: common/mixste.py:278-298).  `img` is [B,H,F,17,3];
+// clamp_hi > 0 applies the sampler's clamp(+-1.1 scale)/scale on the fly (common/diffusionpose.py:136-137,148-149).
+int run_denoiser(d3dp_handle* h, const Workspace& w, const float* x2d, const float* x2d_flip, const float* img,
+                 const long long* t_dev, int B, int H, int n_streams, float clamp_hi, cudaStream_t st) {
+  int rc;
+  if ((rc = ensure_attrs(h))) return rc;
+  const int F = h->cfg.frames, depth = h->cfg.depth;
+  const int T = n_streams * kJ * F;
+
+  time_mlp_kernel<<<B, 512, 0, st>>>(t_dev, F32(h, "time_mlp.1.weight"), F32(h, "time_mlp.1.bias"),
+                                    F32(h, "time_mlp.3.weight"), F32(h, "time_mlp.3.bias"), w.tau);
+  CK(cudaGetLastError());
+
+  EmbedParams ep;
+  ep.x2d = x2d; ep.x2d_flip = x2d_flip; ep.img = img;
+  ep.w_e = F32(h, "Spatial_patch_to_embedding.weight");
+  ep.b_e = F32(h, "Spatial_patch_to_embedding.bias");
+  ep.spos = F32(h, "Spatial_pos_embed");
+  ep.tau = w.tau;
+  ep.ln_g = static_cast<const float*>(h->sblk[0].n1w->dev);
+  ep.ln_b = static_cast<const float*>(h->sblk[0].n1b->dev);
+  ep.ln_eps = 1e-6f;
+  ep.x = w.x; ep.a16 = w.a16;
+  ep.B = B; ep.H = H; ep.F = F; ep.n_streams = n_streams;
+  ep.clamp_hi = clamp_hi; ep.scale = h->cfg.scale;
+  for (int j = 0; j < kJ; ++j) ep.perm[j] = h->cfg.flip_perm[j];
+  {
+    const int blocks = (T + 7) / 8 < h->num_sms * 8 ? (T + 7) / 8 : h->num_sms * 8;
+    embed_kernel<<<blocks, 256, 0, st>>>(ep);
+    CK(cudaGetLastError());
+  }
+
+  CUtensorMap tm_a, tm_o, tm_h;
+  if ((rc = make_tmap(h, &tm_a, w.a16, T, 512, 128))) return rc;
+  if ((rc = make_tmap(h, &tm_o, w.o16, T, 512, 128))) return rc;
+  if ((rc = make_tmap(h, &tm_h, w.qkv16, T, 1024, 128))) return rc;
+
+  const float* ln_s_g = F32(h, "Spatial_norm.weight");
+  const float* ln_s_b = F32(h, "Spatial_norm.bias");
+  const float* ln_t_g = F32(h, "Temporal_norm.weight");
+  const float* ln_t_b = F32(h, "Temporal_norm.bias");
+  const float* tpos = F32(h, "Temporal_pos_embed");
+
+  for (int d = 0; d < depth; ++d) {
+    for (int which = 0; which < 2; ++which) {  // 0 = spatial block, 1 = temporal block
+      const BlockW& bw = which == 0 ? h->sblk[d] : h->tblk[d];
+      GemmParams p{};
+      p.F = F;
+      // qkv = Linear(norm1(x))  (a16 already holds norm1(x))
+      p.M = T; p.N = 1536; p.K = 512;
+      p.bias = static_cast<const float*>(bw.qkvb->dev);
+      p.out16 = w.qkv16; p.ldo = 1536;
+      if ((rc = launch_gemm(h, EPI_BIAS_F16, tm_a, bw.qkvw->tmap, p, st))) return rc;
+      // attention
+      if (which == 0) rc = launch_attn_spatial(h, w.qkv16, w.o16, n_streams, st);
+      else rc = launch_attn_temporal(h, w.qkv16, w.o16, n_streams, st);
+      if (rc) return rc;
+      // x += proj(o) ; a16 = norm2(x)
+      p = GemmParams{};
+      p.F = F; p.M = T; p.N = 512; p.K = 512;
+      p.bias = static_cast<const float*>(bw.projb->dev);
+      p.out16 = w.a16; p.ldo = 512; p.x = w.x;
+      p.ln_a_g = static_cast<const float*>(bw.n2w->dev);
+      p.ln_a_b = static_cast<const float*>(bw.n2b->dev);
+      p.ln_a_eps = 1e-6f;
+      if ((rc = launch_gemm(h, EPI_RES_LN, tm_o, bw.projw->tmap, p, st))) return rc;
+      // hidden = gelu(fc1(a16))
+      p = GemmParams{};
+      p.F = F; p.M = T; p.N = 1024; p.K = 512;
+      p.bias = static_cast<const float*>(bw.fc1b->dev);
+      p.out16 = w.qkv16; p.ldo = 1024;
+      if ((rc = launch_gemm(h, EPI_BIAS_GELU_F16, tm_a, bw.fc1w->tmap, p, st))) return rc;
+      // x = shared_norm(x + fc2(hidden)) (+Tpos after S0) ; a16 = next block's norm1(x)
+      p = GemmParams{};
+      p.F = F; p.M = T; p.N = 512; p.K = 1024;
+      p.bias = static_cast<const float*>(bw.fc2b->dev);
+      p.out16 = w.a16; p.ldo = 512; p.x = w.x;
+      p.ln_a_g = which == 0 ? ln_s_g : ln_t_g;
+      p.ln_a_b = which == 0 ? ln_s_b : ln_t_b;
+      p.ln_a_eps = 1e-6f;
+      p.tpos = (which == 0 && d == 0) ? tpos : nullptr;
+      const BlockW* next = which == 0 ? &h->tblk[d] : (d + 1 < depth ? &h->sblk[d + 1] : nullptr);
+      if (next) {
+        p.ln_b_g = static_cast<const float*>(next->n1w->dev);
+        p.ln_b_b = static_cast<const float*>(next->n1b->dev);
+        p.ln_b_eps = 1e-6f;
+      }
+      if ((rc = launch_gemm(h, EPI_RES_LN2, tm_h, bw.fc2w->tmap, p, st))) return rc;
+    }
+  }
+  {
+    const int blocks = (T + 7) / 8 < h->num_sms * 8 ? (T + 7) / 8 : h->num_sms * 8;
+    head_kernel<<<blocks, 256, 0, st>>>(w.x, F32(h, "head.0.weight"), F32(h, "head.0.bias"), 1e-5f,
+                                       F32(h, "head.1.weight"), F32(h, "head.1.bias"), w.den, n_streams, F);
+    CK(cudaGetLastError());
+  }
+  return D3DP_OK;
+}
+
+int check_ready(d3dp_handle* h) {
+  if (d3dp_weights_missing(h) != 0) return fail(h, D3DP_E_WEIGHTS, "weights incomplete: call d3dp_set_weight for every tensor");
+  return D3DP_OK;
+}
+
+int grid_for(long long n, int num_sms) {
+  long long b = (n + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms) * 8;
+  return static_cast<int>(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace
+
+// =====================================================================================================  C ABI
+extern "C" {
+
+const char* d3dp_version(void) { return "d3dp_b200 0.1.0 sm_100a"; }
+
+int d3dp_create(const d3dp_config* cfg, d3dp_handle** out) {
+  if (!cfg || !out) return D3DP_E_INVALID;
+  *out = nullptr;
+  if (cfg->joints != 17 || cfg->channels != 512 || cfg->heads != 8 || cfg->mlp_hidden != 1024 ||
+      cfg->depth < 1 || cfg->depth > 8 || cfg->frames < 1 || cfg->frames > 256 || cfg->num_timesteps < 1)
+    return D3DP_E_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return D3DP_E_CUDA;
+  d3dp_handle* h = new d3dp_handle();
+  h->cfg = *cfg;
+  cudaGetDevice(&h->device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess || prop.major != 10) {
+    delete h;
+    return D3DP_E_CUDA;  // sm_100a only: no fallback path exists
+  }
+  h->num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+    delete h;
+    return D3DP_E_CUDA;
+  }
+  h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+
+  const int C = 512, F = cfg->frames;
+  add_slot(h, "Spatial_patch_to_embedding.weight", C * 5);
+  add_slot(h, "Spatial_patch_to_embedding.bias", C);
+  add_slot(h, "Spatial_pos_embed", 17 * C);
+  add_slot(h, "Temporal_pos_embed", static_cast<int64_t>(F) * C);
+  add_slot(h, "time_mlp.1.weight", 2 * C * C);
+  add_slot(h, "time_mlp.1.bias", 2 * C);
+  add_slot(h, "time_mlp.3.weight", 2 * C * C);
+  add_slot(h, "time_mlp.3.bias", C);
+  for (int d = 0; d < cfg->depth; ++d) add_block(h, "STEblocks." + std::to_string(d) + ".", h->sblk);
+  for (int d = 0; d < cfg->depth; ++d) add_block(h, "TTEblocks." + std::to_string(d) + ".", h->tblk);
+  for (int d = 0; d < cfg->depth; ++d) {
+    bind_block(h, "STEblocks." + std::to_string(d) + ".", h->sblk[d]);
+    bind_block(h, "TTEblocks." + std::to_string(d) + ".", h->tblk[d]);
+  }
+  add_slot(h, "Spatial_norm.weight", C);
+  add_slot(h, "Spatial_norm.bias", C);
+  add_slot(h, "Temporal_norm.weight", C);
+  add_slot(h, "Temporal_norm.bias", C);
+  add_slot(h, "head.0.weight", C);
+  add_slot(h, "head.0.bias", C);
+  add_slot(h, "head.1.weight", 3 * C);
+  add_slot(h, "head.1.bias", 3);
+  // bind again: std::map nodes are stable, but the blocks were bound before all inserts only by name lookups
+  for (auto& kv : h->slots) {
+    Slot& s = kv.second;
+    const size_t bytes = static_cast<size_t>(s.numel) * (s.f16 ? 2 : 4);
+    if (cudaMalloc(&s.dev, bytes) != cudaSuccess) {
+      d3dp_destroy(h);
+      return D3DP_E_CUDA;
+    }
+  }
+  compute_schedule(h);
+  if (upload_schedule(h) != D3DP_OK) {
+    d3dp_destroy(h);
+    return D3DP_E_CUDA;
+  }
+  *out = h;
+  return D3DP_OK;
+}
+
+void d3dp_destroy(d3dp_handle* h) {
+  if (!h) return;
+  for (auto& kv : h->slots)
+    if (kv.second.dev) cudaFree(kv.second.dev);
+  if (h->d_sqrt_ac) cudaFree(h->d_sqrt_ac);
+  if (h->d_sqrt_1mac) cudaFree(h->d_sqrt_1mac);
+  delete h;
+}
+
+const char* d3dp_last_error(const d3dp_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int d3dp_set_weight(d3dp_handle* h, const char* name, const float* data, int64_t numel, void* stream) {
+  if (!h || !name || !data) return D3DP_E_INVALID;
+  auto it = h->slots.find(name);
+  if (it == h->slots.end()) return fail(h, D3DP_E_WEIGHTS, std::string("unknown weight name: ") + name);
+  Slot& s = it->second;
+  if (s.numel != numel)
+    return fail(h, D3DP_E_WEIGHTS, std::string("size mismatch for ") + name + ": expected " +
+                                       std::to_string(s.numel) + ", got " + std::to_string(numel));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (s.f16) {
+    f32_to_f16_kernel<<<grid_for(numel, h->num_sms), 256, 0, st>>>(data, static_cast<__half*>(s.dev),
+                                                                   static_cast<size_t>(numel));
+    CK(cudaGetLastError());
+    int rc = make_tmap(h, &s.tmap, s.dev, s.rows, s.cols, 256);
+    if (rc) return rc;
+  } else {
+    CK(cudaMemcpyAsync(s.dev, data, static_cast<size_t>(numel) * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  s.set = true;
+  return D3DP_OK;
+}
+
+int d3dp_weights_missing(const d3dp_handle* h) {
+  if (!h) return -1;
+  int n = 0;
+  for (auto& kv : h->slots) n += kv.second.set ? 0 : 1;
+  return n;
+}
+
+int d3dp_set_schedule(d3dp_handle* h, const double* ac, const double* sr, const double* srm1, const double* sac,
+                      const double* s1mac, int32_t n) {
+  if (!h || !ac || !sr || !srm1 || !sac || !s1mac || n != h->cfg.num_timesteps) return D3DP_E_INVALID;
+  h->ac.assign(ac, ac + n);
+  h->sqrt_recip.assign(sr, sr + n);
+  h->sqrt_recipm1.assign(srm1, srm1 + n);
+  h->sqrt_ac.assign(sac, sac + n);
+  h->sqrt_1mac.assign(s1mac, s1mac + n);
+  return upload_schedule(h);
+}
+
+int d3dp_get_alphas_cumprod(const d3dp_handle* h, double* out, int32_t n) {
+  if (!h || !out || n != static_cast<int32_t>(h->ac.size())) return D3DP_E_INVALID;
+  std::memcpy(out, h->ac.data(), sizeof(double) * n);
+  return D3DP_OK;
+}
+
+int d3dp_time_list(int32_t num_timesteps, int32_t K, int32_t* out) {
+  if (!out || K < 1 || num_timesteps < 1) return D3DP_E_INVALID;
+  // torch.linspace(-1, T-1, K+1) in float32: step = (end-start)/(steps-1); the first half counts up from start,
+  // the second half counts down from end; .int() truncates toward zero; the list is then reversed.
+  const int steps = K + 1;
+  const float start = -1.0f, end = static_cast<float>(num_timesteps - 1);
+  const float step = (end - start) / static_cast<float>(steps - 1);
+  const int halfway = steps / 2;
+  for (int i = 0; i < steps; ++i) {
+    const float v = i < halfway ? start + step * static_cast<float>(i) : end - step * static_cast<float>(steps - i - 1);
+    out[steps - 1 - i] = static_cast<int32_t>(v);
+  }
+  return D3DP_OK;
+}
+
+int d3dp_workspace_bytes(const d3dp_handle* h, int32_t B, int32_t H, int32_t flip, size_t* bytes) {
+  if (!h || !bytes || B < 1 || H < 1) return D3DP_E_INVALID;
+  const int n_streams = B * H * (flip ? 2 : 1);
+  *bytes = carve(h, nullptr, B, H, n_streams).bytes;
+  return D3DP_OK;
+}
+
+int d3dp_denoise(d3dp_handle* h, const float* x2d, const float* x_t, const int64_t* t, float* out, int32_t B,
+                 int32_t H, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !x2d || !x_t || !t || !out || !workspace || B < 1 || H < 1) return fail(h, D3DP_E_INVALID, "denoise: bad argument");
+  int rc;
+  if ((rc = check_ready(h))) return rc;
+  Workspace w = carve(h, workspace, B, H, B * H);
+  if (w.bytes > workspace_bytes) return fail(h, D3DP_E_WORKSPACE, "denoise: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = run_denoiser(h, w, x2d, nullptr, x_t, reinterpret_cast<const long long*>(t), B, H, B * H, 0.f, st))) return rc;
+  CK(cudaMemcpyAsync(out, w.den, static_cast<size_t>(B) * H * h->cfg.frames * kJ * 3 * 4, cudaMemcpyDeviceToDevice, st));
+  return D3DP_OK;
+}
+
+int d3dp_ddim_sample(d3dp_handle* h, const float* x2d, const float* x2d_flip, const float* noise_init,
+                     const float* noise_steps, uint64_t seed, int32_t h_offset, int32_t H_total,
+                     const int32_t* timesteps_host, float* preds, int32_t B, int32_t H, int32_t K, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  if (!h || !x2d || !preds || !workspace || B < 1 || H < 1 || K < 1 || K > h->cfg.num_timesteps)
+    return fail(h, D3DP_E_INVALID, "ddim_sample: bad argument");
+  if (H_total < h_offset + H) return fail(h, D3DP_E_INVALID, "ddim_sample: h_offset + H exceeds H_total");
+  int rc;
+  if ((rc = check_ready(h))) return rc;
+  const int flip = x2d_flip ? 1 : 0;
+  const int n_streams = B * H * (flip ? 2 : 1);
+  Workspace w = carve(h, workspace, B, H, n_streams);
+  if (w.bytes > workspace_bytes) return fail(h, D3DP_E_WORKSPACE, "ddim_sample: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int F = h->cfg.frames;
+  const long long per_bh = static_cast<long long>(F) * kJ * 3;
+  const long long n_img = static_cast<long long>(B) * H * per_bh;
+
+  std::vector<int32_t> times(K + 1);
+  if (timesteps_host) {
+    std::memcpy(times.data(), timesteps_host, sizeof(int32_t) * (K + 1));
+  } else {
+    d3dp_time_list(h->cfg.num_timesteps, K, times.data());
+  }
+  for (int k = 0; k < K; ++k)
+    if (times[k] < 0 || times[k] >= h->cfg.num_timesteps || times[k + 1] >= times[k] || (k + 1 < K && times[k + 1] < 0))
+      return fail(h, D3DP_E_INVALID, "ddim_sample: bad timestep list");
+
+  // img ~ N(0, I)  (common/diffusionpose.py:225)
+  if (noise_init) {
+    CK(cudaMemcpyAsync(w.img, noise_init, static_cast<size_t>(n_img) * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    philox_fill_kernel<<<grid_for(n_img, h->num_sms), 256, 0, st>>>(w.img, B, H, per_bh, seed, h_offset, H_total, 0u);
+    CK(cudaGetLastError());
+  }
+  const float scale = h->cfg.scale;
+  for (int k = 0; k < K; ++k) {
+    const int t = times[k], t_next = times[k + 1];
+    fill_t_kernel<<<(B + 127) / 128, 128, 0, st>>>(w.t, B, static_cast<long long>(t));
+    CK(cudaGetLastError());
+    if ((rc = run_denoiser(h, w, x2d, x2d_flip, w.img, w.t, B, H, n_streams, 1.1f * scale, st))) return rc;
+    DdimParams dp{};
+    dp.den = w.den; dp.img = w.img; dp.preds = preds;
+    dp.noise = (noise_steps && t_next >= 0) ? noise_steps + static_cast<size_t>(k) * n_img : nullptr;
+    dp.B = B; dp.H = H; dp.K = K; dp.F = F; dp.k = k;
+    dp.flip = flip; dp.last = t_next < 0 ? 1 : 0;
+    dp.scale = scale;
+    dp.sqrt_recip_ac = h->sqrt_recip[t];
+    dp.sqrt_recipm1_ac = h->sqrt_recipm1[t];
+    if (t_next >= 0) {
+      // eta = 1 DDIM coefficients in float64 (common/diffusionpose.py:244-248)
+      const double a = h->ac[t], an = h->ac[t_next];
+      const double sigma = 1.0 * std::sqrt((1 - a / an) * (1 - an) / (1 - a));
+      const double c = std::sqrt(1 - an - sigma * sigma);
+      dp.sigma = static_cast<float>(sigma);
+      dp.c = static_cast<float>(c);
+      dp.sqrt_ac_next = static_cast<float>(std::sqrt(an));
+    }
+    dp.seed = seed; dp.h_offset = h_offset; dp.H_total = H_total;
+    for (int j = 0; j < kJ; ++j) dp.perm[j] = h->cfg.flip_perm[j];
+    ddim_step_kernel<<<grid_for(n_img, h->num_sms), 256, 0, st>>>(dp);
+    CK(cudaGetLastError());
+  }
+  return D3DP_OK;
+}
+
+int d3dp_q_sample(d3dp_handle* h, const float* x0, const float* noise, const int64_t* t, float* out, int32_t B,
+                  int64_t per_sample, int32_t clamp, void* stream) {
+  if (!h || !x0 || !noise || !t || !out || B < 1 || per_sample < 1) return fail(h, D3DP_E_INVALID, "q_sample: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float scale = h->cfg.scale;
+  q_sample_kernel<<<grid_for(B * per_sample, h->num_sms), 256, 0, st>>>(
+      x0, noise, reinterpret_cast<const long long*>(t), h->d_sqrt_ac, h->d_sqrt_1mac, out, B, per_sample,
+      clamp ? scale : 1.0f, clamp ? 1.1f * scale : 0.f, scale);
+  CK(cudaGetLastError());
+  return D3DP_OK;
+}
+
+int d3dp_jpma(d3dp_handle* h, const float* preds, const float* traj, const float* cam, const float* x2d,
+              float* jagg_pose, int32_t* jagg_idx, float* pagg_pose, float* e2d_min, int32_t B, int32_t K, int32_t H,
+              int32_t root_joint, int32_t linear, void* stream) {
+  if (!h || !preds || !traj || !cam || !x2d || !jagg_pose || !jagg_idx || !pagg_pose || B < 1 || K < 1 || H < 1)
+    return fail(h, D3DP_E_INVALID, "jpma: bad argument");
+  JpmaParams p;
+  p.pred = preds; p.traj = traj; p.cam = cam; p.x2d = x2d;
+  p.jagg_pose = jagg_pose; p.jagg_idx = jagg_idx; p.pagg_pose = pagg_pose; p.e2d_min = e2d_min;
+  p.B = B; p.K = K; p.H = H; p.F = h->cfg.frames; p.root = root_joint; p.linear = linear;
+  const long long n = static_cast<long long>(B) * K * p.F * kJ;
+  jpma_kernel<<<grid_for(n, h->num_sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  CK(cudaGetLastError());
+  return D3DP_OK;
+}
+
+int d3dp_philox_normal(d3dp_handle* h, float* out, int32_t B, int32_t H, int64_t per_bh, uint64_t seed,
+                       int32_t h_offset, int32_t H_total, uint32_t draw, void* stream) {
+  if (!h || !out || B < 1 || H < 1 || per_bh < 1) return fail(h, D3DP_E_INVALID, "philox: bad argument");
+  philox_fill_kernel<<<grid_for(static_cast<long long>(B) * H * per_bh, h->num_sms), 256, 0,
+                       static_cast<cudaStream_t>(stream)>>>(out, B, H, per_bh, seed, h_offset, H_total, draw);
+  CK(cudaGetLastError());
+  return D3DP_OK;
+}
+
+int d3dp_test_gemm(d3dp_handle* h, int32_t mode, const void* a16, const void* w16, const float* bias, void* out16,
+                   float* x, const float* g_a, const float* b_a, float eps_a, const float* g_b, const float* b_b,
+                   float eps_b, const float* tpos, int32_t F, int32_t M, int32_t N, int32_t K, void* stream) {
+  if (!h || !a16 || !w16 || !bias) return fail(h, D3DP_E_INVALID, "test_gemm: bad argument");
+  int rc;
+  if ((rc = ensure_attrs(h))) return rc;
+  CUtensorMap tmA, tmB;
+  if ((rc = make_tmap(h, &tmA, a16, M, K, 128))) return rc;
+  if ((rc = make_tmap(h, &tmB, w16, N, K, 256))) return rc;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.bias = bias;
+  p.out16 = static_cast<__half*>(out16);
+  p.ldo = N; p.x = x;
+  p.ln_a_g = g_a; p.ln_a_b = b_a; p.ln_a_eps = eps_a;
+  p.ln_b_g = g_b; p.ln_b_b = b_b; p.ln_b_eps = eps_b;
+  p.tpos = tpos; p.F = F > 0 ? F : 1;
+  return launch_gemm(h, mode, tmA, tmB, p, static_cast<cudaStream_t>(stream));
+}
+
+int d3dp_test_attn(d3dp_handle* h, int32_t temporal, const void* qkv16, void* o16, int32_t n_streams, void* stream) {
+  if (!h || !qkv16 || !o16 || n_streams < 1) return fail(h, D3DP_E_INVALID, "test_attn: bad argument");
+  int rc;
+  if ((rc = ensure_attrs(h))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return temporal ? launch_attn_temporal(h, static_cast<const __half*>(qkv16), static_cast<__half*>(o16), n_streams, st)
+                  : launch_attn_spatial(h, static_cast<const __half*>(qkv16), static_cast<__half*>(o16), n_streams, st);
+}
+
+}  // extern "C"

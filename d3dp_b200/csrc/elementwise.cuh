@@ -1,0 +1,406 @@
+// CUDA-core kernels around the GEMM/attention pipeline: timestep MLP, input embedding (+flip TTA on the fly),
+// regression head, the fused DDIM step, forward noising (q_sample), JPMA aggregation, Philox noise and the
+// fp32 -> fp16 weight packer.  Each kernel cites the reference lines it restates.
+#pragma once
+#include "ptx.cuh"
+
+namespace d3dp {
+
+constexpr int kJ = 17;
+constexpr int kC = 512;
+
+// ------------------------------------------------------------------------------------------------ Philox4x32-10
+// Counter-based noise so that hypothesis h of clip b gets the same normals whatever GPU computes it
+// (counter = element index inside [B, H_total, F, 17, 3] + draw index; key = seed).
+struct Philox4 { uint32_t x, y, z, w; };
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
+  return static_cast<uint32_t>((static_cast<uint64_t>(a) * b) >> 32);
+}
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(Philox4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = Philox4{hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0};
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+// One standard normal for (seed, draw, global element index): Box-Muller on two of the four Philox words.
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t draw, uint64_t elem) {
+  Philox4 c{static_cast<uint32_t>(elem), static_cast<uint32_t>(elem >> 32), draw, 0u};
+  c = philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  const float u1 = (static_cast<float>(c.x >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+  const float u2 = (static_cast<float>(c.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+__global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] = __float2half_rn(src[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ timestep MLP
+// tau[b,:] = W2 . gelu(W1 . [sin(t w), cos(t w)] + b1) + b2 , w_i = exp(-i ln(1e4)/255)
+// (reference: common/mixste.py:127-139 SinusoidalPositionEmbeddings, :179-184 time_mlp).  One CTA per batch entry.
+__global__ void __launch_bounds__(512) time_mlp_kernel(const long long* __restrict__ t, const float* __restrict__ w1,
+                                                       const float* __restrict__ b1, const float* __restrict__ w2,
+                                                       const float* __restrict__ b2, float* __restrict__ tau) {
+  __shared__ float emb[512];
+  __shared__ float hid[1024];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float tv = static_cast<float>(t[b]);
+  {
+    const int i = tid & 255;
+    const float w = expf(static_cast<float>(i) * -(logf(10000.0f) / 255.0f));
+    const float a = tv * w;
+    emb[tid] = tid < 256 ? sinf(a) : cosf(a);
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int o = warp; o < 1024; o += 16) {  // warp per output: coalesced weight rows
+    const float* wr = w1 + static_cast<size_t>(o) * 512;
+    float acc = 0.f;
+    for (int k = lane; k < 512; k += 32) acc += wr[k] * emb[k];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0) {
+      const float v = acc + b1[o];
+      hid[o] = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    }
+  }
+  __syncthreads();
+  for (int o = warp; o < 512; o += 16) {
+    const float* wr = w2 + static_cast<size_t>(o) * 1024;
+    float acc = 0.f;
+    for (int k = lane; k < 1024; k += 32) acc += wr[k] * hid[k];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0) tau[static_cast<size_t>(b) * 512 + o] = acc + b2[o];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ embedding
+// x[row,:] = W_e . [x2d(2), x_t(3)] + b_e + Spatial_pos_embed[j] + tau[b]   and   a16 = fp16(LN_norm1(x))
+// (reference: common/mixste.py:226-236 eval branch of STE_forward, then STEblocks[0].norm1, :114).
+// Streams: s in [0, B*H) read (x2d, clamp(img)/scale); with flip TTA streams [B*H, 2*B*H) read
+// (x2d_flip, flip(clamp(img)/scale)) where flip negates coordinate 0 and swaps left/right joints
+// (reference: common/diffusionpose.py:148-153).  Token order out: row = (s*17 + j)*F + f.  One warp per token.
+struct EmbedParams {
+  const float* x2d;       // [B,F,17,2]
+  const float* x2d_flip;  // [B,F,17,2] or null
+  const float* img;       // [B,H,F,17,3]
+  const float* w_e;       // [512,5]
+  const float* b_e;       // [512]
+  const float* spos;      // [17,512]
+  const float* tau;       // [B,512]
+  const float* ln_g;      // STEblocks[0].norm1
+  const float* ln_b;
+  float ln_eps;
+  float* x;               // [T,512]
+  __half* a16;            // [T,512]
+  int B, H, F;
+  int n_streams;          // B*H or 2*B*H
+  float clamp_hi;         // 1.1*scale  (<=0: no clamp, plain denoise entry)
+  float scale;
+  int perm[kJ];           // joint permutation of the flip
+};
+
+__global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int BH = p.B * p.H;
+  const long long T = static_cast<long long>(p.n_streams) * kJ * p.F;
+  for (long long row = warp; row < T; row += nwarps) {
+    const int f = static_cast<int>(row % p.F);
+    const long long sj = row / p.F;
+    const int j = static_cast<int>(sj % kJ);
+    const int s = static_cast<int>(sj / kJ);
+    const bool flip = s >= BH;
+    const int bh = flip ? s - BH : s;
+    const int b = bh / p.H;
+    float in[5];
+    {
+      const float* src2 = (flip ? p.x2d_flip : p.x2d) + ((static_cast<size_t>(b) * p.F + f) * kJ + j) * 2;
+      in[0] = src2[0];
+      in[1] = src2[1];
+      const int js = flip ? p.perm[j] : j;
+      const float* src3 = p.img + ((static_cast<size_t>(bh) * p.F + f) * kJ + js) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v = src3[c];
+        if (p.clamp_hi > 0.f) v = __fdiv_rn(fminf(fmaxf(v, -p.clamp_hi), p.clamp_hi), p.scale);
+        in[2 + c] = v;
+      }
+      if (flip) in[2] = -in[2];
+    }
+    float v[16];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = i * 32 + lane;
+      const float* w = p.w_e + c * 5;
+      float acc = p.b_e[c];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) acc += w[k] * in[k];
+      acc += p.spos[j * kC + c] + p.tau[static_cast<size_t>(b) * kC + c];
+      v[i] = acc;
+      sum += acc;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    const float mean = sum * (1.0f / kC);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sq += (v[i] - mean) * (v[i] - mean);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
+    const float rstd = rsqrtf(sq * (1.0f / kC) + p.ln_eps);
+    float* xr = p.x + row * kC;
+    __half* ar = p.a16 + row * kC;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = i * 32 + lane;
+      xr[c] = v[i];
+      ar[c] = __float2half_rn((v[i] - mean) * rstd * p.ln_g[c] + p.ln_b[c]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ head
+// out[s, f, j, :] = W_h . LN(x[row,:]; eps 1e-5) + b_h   (reference: common/mixste.py:207-210,291-296)
+// x rows are in [S, J, F] order; out is written in the reference's [.., F, 17, 3] order. One warp per token.
+__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ x, const float* __restrict__ ln_g,
+                                                   const float* __restrict__ ln_b, float ln_eps,
+                                                   const float* __restrict__ w_h, const float* __restrict__ b_h,
+                                                   float* __restrict__ out, int n_streams, int F) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const long long T = static_cast<long long>(n_streams) * kJ * F;
+  for (long long row = warp; row < T; row += nwarps) {
+    const float* xr = x + row * kC;
+    float v[16];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      v[i] = xr[i * 32 + lane];
+      sum += v[i];
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    const float mean = sum * (1.0f / kC);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sq += (v[i] - mean) * (v[i] - mean);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
+    const float rstd = rsqrtf(sq * (1.0f / kC) + ln_eps);
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = i * 32 + lane;
+      const float y = (v[i] - mean) * rstd * ln_g[c] + ln_b[c];
+      o0 += y * w_h[c];
+      o1 += y * w_h[kC + c];
+      o2 += y * w_h[2 * kC + c];
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      o0 += __shfl_xor_sync(0xffffffffu, o0, d);
+      o1 += __shfl_xor_sync(0xffffffffu, o1, d);
+      o2 += __shfl_xor_sync(0xffffffffu, o2, d);
+    }
+    if (lane == 0) {
+      const int f = static_cast<int>(row % F);
+      const long long sj = row / F;
+      const int j = static_cast<int>(sj % kJ);
+      const long long s = sj / kJ;
+      float* o = out + ((s * F + f) * kJ + j) * 3;
+      o[0] = o0 + b_h[0];
+      o[1] = o1 + b_h[1];
+      o[2] = o2 + b_h[2];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ DDIM step
+// One sampler step after the denoiser (reference: common/diffusionpose.py:158-167 un-flip/average/x0/eps and
+// :238-254 the eta=1 DDIM update).  den holds the denoiser output for the plain streams [0,BH) and, with TTA,
+// the flipped streams [BH,2BH).  eps is formed in float64 from the float64 schedule buffers then rounded to
+// float32, exactly like the reference's promoted expression; the three products of the update are rounded
+// separately (no FMA contraction) like the reference's eager ops.
+struct DdimParams {
+  const float* den;     // [n_streams, F, 17, 3]
+  float* img;           // [B,H,F,17,3] state, updated in place
+  float* preds;         // [B,K,H,F,17,3]
+  const float* noise;   // injected N(0,1) for this step [B,H,F,17,3] or null -> Philox
+  int B, H, K, F, k;
+  int flip;             // 1: TTA streams present
+  int last;             // 1: img = x0
+  float scale;
+  double sqrt_recip_ac, sqrt_recipm1_ac;
+  float sqrt_ac_next, c, sigma;
+  unsigned long long seed;
+  int h_offset, H_total;  // global hypothesis index = h_offset + h (Philox addressing)
+  int perm[kJ];
+};
+
+__global__ void __launch_bounds__(256) ddim_step_kernel(const DdimParams p) {
+  const long long per_bh = static_cast<long long>(p.F) * kJ * 3;
+  const long long n = static_cast<long long>(p.B) * p.H * per_bh;
+  const long long BH = static_cast<long long>(p.B) * p.H;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % 3);
+    const int j = static_cast<int>((i / 3) % kJ);
+    const long long bhf = i / (3 * kJ);
+    const int f = static_cast<int>(bhf % p.F);
+    const long long bh = bhf / p.F;
+    float pred = p.den[i];
+    if (p.flip) {
+      float o2 = p.den[((BH + bh) * p.F + f) * (kJ * 3) + p.perm[j] * 3 + c];
+      if (c == 0) o2 = -o2;
+      pred = __fdiv_rn(__fadd_rn(pred, o2), 2.0f);
+    }
+    float x0 = __fmul_rn(pred, p.scale);
+    x0 = fminf(fmaxf(x0, -1.1f * p.scale), 1.1f * p.scale);
+    const int b = static_cast<int>(bh / p.H), h = static_cast<int>(bh % p.H);
+    p.preds[(((static_cast<long long>(b) * p.K + p.k) * p.H + h) * per_bh) + (i - bh * per_bh)] = x0;
+    if (p.last) {
+      p.img[i] = x0;
+    } else {
+      const float xi = p.img[i];
+      const float eps = static_cast<float>((p.sqrt_recip_ac * static_cast<double>(xi) - static_cast<double>(x0)) /
+                                           p.sqrt_recipm1_ac);
+      float z;
+      if (p.noise) {
+        z = p.noise[i];
+      } else {
+        const unsigned long long ge =
+            (static_cast<unsigned long long>(b) * p.H_total + (p.h_offset + h)) * per_bh + (i - bh * per_bh);
+        z = philox_normal(p.seed, static_cast<uint32_t>(p.k + 1), ge);
+      }
+      p.img[i] = __fadd_rn(__fadd_rn(__fmul_rn(x0, p.sqrt_ac_next), __fmul_rn(p.c, eps)), __fmul_rn(p.sigma, z));
+    }
+  }
+}
+
+// initial state img ~ N(0,I) (reference: common/diffusionpose.py:225) from Philox, draw index 0
+__global__ void philox_fill_kernel(float* __restrict__ img, int B, int H, long long per_bh, unsigned long long seed,
+                                   int h_offset, int H_total, unsigned draw) {
+  const long long n = static_cast<long long>(B) * H * per_bh;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long bh = i / per_bh;
+    const int b = static_cast<int>(bh / H), h = static_cast<int>(bh % H);
+    const unsigned long long ge =
+        (static_cast<unsigned long long>(b) * H_total + (h_offset + h)) * per_bh + (i - bh * per_bh);
+    img[i] = philox_normal(seed, draw, ge);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ q_sample
+// x_t = sqrt(acp_t) * x0 + sqrt(1-acp_t) * noise, optionally clamp(+-1.1 scale)/scale
+// (reference: common/diffusionpose.py:260-267 q_sample and :290-306 prepare_diffusion_concat). t per sample.
+__global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                                const long long* __restrict__ t, const double* __restrict__ sqrt_ac,
+                                const double* __restrict__ sqrt_1mac, float* __restrict__ out, int B,
+                                long long per_b, float in_scale, float clamp_hi, float out_div) {
+  const long long n = static_cast<long long>(B) * per_b;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / per_b);
+    const long long tt = t[b];
+    // the reference multiplies float64 buffers into float32 tensors -> float64 arithmetic
+    double v = sqrt_ac[tt] * static_cast<double>(__fmul_rn(x0[i], in_scale)) +
+               sqrt_1mac[tt] * static_cast<double>(noise[i]);
+    if (clamp_hi > 0.f) {
+      v = fmin(fmax(v, -static_cast<double>(clamp_hi)), static_cast<double>(clamp_hi));
+      v = v / static_cast<double>(out_div);
+    }
+    out[i] = static_cast<float>(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ JPMA
+// Joint-wise reprojection-based multi-hypothesis aggregation (reference: main.py:700-712 root zero + trajectory +
+// project; common/camera.py:44-60 project_to_2d; common/loss.py:54-76 argmin over hypotheses of the 2D error;
+// main_3dhp.py:782 P-Agg mean, :801-835 pose-level J-Agg gather).  One thread per (b,k,f,j), loop over H.
+struct JpmaParams {
+  const float* pred;   // [B,K,H,F,17,3]
+  const float* traj;   // [B,F,3]
+  const float* cam;    // [B,9]  (f2, c2, k3, p2)
+  const float* x2d;    // [B,F,17,2]
+  float* jagg_pose;    // [B,K,F,17,3]
+  int* jagg_idx;       // [B,K,F,17]
+  float* pagg_pose;    // [B,K,F,17,3]
+  float* e2d_min;      // [B,K,F,17] or null
+  int B, K, H, F, root;
+  int linear;          // 1: project_to_2d_linear (focal + principal point only)
+};
+
+__global__ void __launch_bounds__(256) jpma_kernel(const JpmaParams p) {
+  const long long n = static_cast<long long>(p.B) * p.K * p.F * kJ;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(i % kJ);
+    const int f = static_cast<int>((i / kJ) % p.F);
+    const int k = static_cast<int>((i / (static_cast<long long>(kJ) * p.F)) % p.K);
+    const int b = static_cast<int>(i / (static_cast<long long>(kJ) * p.F * p.K));
+    const float* tr = p.traj + (static_cast<size_t>(b) * p.F + f) * 3;
+    const float* cm = p.cam + static_cast<size_t>(b) * 9;
+    const float u = p.x2d[((static_cast<size_t>(b) * p.F + f) * kJ + j) * 2];
+    const float v = p.x2d[((static_cast<size_t>(b) * p.F + f) * kJ + j) * 2 + 1];
+    float best = INFINITY;
+    int best_h = 0;
+    float bx = 0.f, by = 0.f, bz = 0.f;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int h = 0; h < p.H; ++h) {
+      const float* q =
+          p.pred + ((((static_cast<size_t>(b) * p.K + k) * p.H + h) * p.F + f) * kJ + j) * 3;
+      float px = q[0], py = q[1], pz = q[2];
+      if (j == p.root) px = py = pz = 0.f;
+      sx = __fadd_rn(sx, px);
+      sy = __fadd_rn(sy, py);
+      sz = __fadd_rn(sz, pz);
+      const float X = __fadd_rn(px, tr[0]), Y = __fadd_rn(py, tr[1]), Z = __fadd_rn(pz, tr[2]);
+      const float xx = fminf(fmaxf(__fdiv_rn(X, Z), -1.f), 1.f);
+      const float yy = fminf(fmaxf(__fdiv_rn(Y, Z), -1.f), 1.f);
+      float pu, pv;
+      if (p.linear) {
+        pu = __fadd_rn(__fmul_rn(cm[0], xx), cm[2]);
+        pv = __fadd_rn(__fmul_rn(cm[1], yy), cm[3]);
+      } else {
+        const float r2 = __fadd_rn(__fmul_rn(xx, xx), __fmul_rn(yy, yy));
+        const float r4 = __fmul_rn(r2, r2), r6 = __fmul_rn(__fmul_rn(r2, r2), r2);
+        const float radial =
+            __fadd_rn(1.f, __fadd_rn(__fadd_rn(__fmul_rn(cm[4], r2), __fmul_rn(cm[5], r4)), __fmul_rn(cm[6], r6)));
+        const float tan = __fadd_rn(__fmul_rn(cm[7], xx), __fmul_rn(cm[8], yy));
+        const float rt = __fadd_rn(radial, tan);
+        const float X3 = __fadd_rn(__fmul_rn(xx, rt), __fmul_rn(cm[7], r2));
+        const float Y3 = __fadd_rn(__fmul_rn(yy, rt), __fmul_rn(cm[8], r2));
+        pu = __fadd_rn(__fmul_rn(cm[0], X3), cm[2]);
+        pv = __fadd_rn(__fmul_rn(cm[1], Y3), cm[3]);
+      }
+      const float du = __fsub_rn(pu, u), dv = __fsub_rn(pv, v);
+      const float e = __fsqrt_rn(__fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)));
+      if (e < best) {  // strict: first index wins ties, like torch.min
+        best = e;
+        best_h = h;
+        bx = px; by = py; bz = pz;
+      }
+    }
+    float* jo = p.jagg_pose + i * 3;
+    jo[0] = bx; jo[1] = by; jo[2] = bz;
+    p.jagg_idx[i] = best_h;
+    const float invH = 1.0f / static_cast<float>(p.H);
+    float* po = p.pagg_pose + i * 3;
+    po[0] = sx * invH; po[1] = sy * invH; po[2] = sz * invH;
+    if (p.e2d_min) p.e2d_min[i] = best;
+  }
+}
+
+}  // namespace d3dp

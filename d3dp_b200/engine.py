@@ -1,0 +1,176 @@
+"""Thin Python owner of a `d3dp_handle` (include/d3dp_b200.h): weight upload, workspace, and one method per C entry
+point.  PyTorch is used only for device memory and the CUDA stream; every computation is inside libd3dp_b200.so."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import D3dpConfig, D3dpError, check, ptr
+
+H36M_JOINTS_LEFT = [4, 5, 6, 11, 12, 13]
+H36M_JOINTS_RIGHT = [1, 2, 3, 14, 15, 16]
+
+
+def flip_permutation(joints_left, joints_right, n=17):
+    """perm[j] = source joint of j under x[..., L+R, :] = x[..., R+L, :] (common/diffusionpose.py:152-153)."""
+    perm = list(range(n))
+    for dst, src in zip(list(joints_left) + list(joints_right), list(joints_right) + list(joints_left)):
+        perm[dst] = src
+    return perm
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    def __init__(self, frames, joints_left=H36M_JOINTS_LEFT, joints_right=H36M_JOINTS_RIGHT, depth=8, channels=512,
+                 scale=1.0, num_timesteps=1000, device=None):
+        if not torch.cuda.is_available():
+            raise D3dpError("d3dp_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.frames, self.depth, self.scale, self.num_timesteps = frames, depth, float(scale), num_timesteps
+        cfg = D3dpConfig()
+        cfg.frames, cfg.joints, cfg.channels, cfg.depth = frames, 17, channels, depth
+        cfg.heads, cfg.mlp_hidden, cfg.num_timesteps, cfg.scale = 8, 2 * channels, num_timesteps, float(scale)
+        for j, s in enumerate(flip_permutation(joints_left, joints_right)):
+            cfg.flip_perm[j] = s
+        self.handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.d3dp_create(C.byref(cfg), C.byref(self.handle))
+        if rc != 0:
+            raise D3dpError(f"d3dp_create failed (code {rc}): needs an sm_100 GPU, C=512, F<=256, depth<=8")
+        self._ws = None
+        self._keep = []
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and self.handle.value:
+                self.lib.d3dp_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights / schedule
+    def load_pose_estimator_state(self, state):
+        """`state`: {name: tensor} with the reference's `pose_estimator.*` keys (prefix stripped)."""
+        with torch.cuda.device(self.device):
+            for name, t in state.items():
+                t = t.detach().to(self.device, torch.float32).contiguous()
+                check(self.handle, self.lib.d3dp_set_weight(self.handle, name.encode(), ptr(t), t.numel(), _stream()),
+                      f"d3dp_set_weight({name})")
+            torch.cuda.current_stream().synchronize()
+        missing = self.lib.d3dp_weights_missing(self.handle)
+        if missing:
+            raise D3dpError(f"{missing} weight tensors missing after load")
+
+    def set_schedule(self, alphas_cumprod, sqrt_recip, sqrt_recipm1, sqrt_ac, sqrt_1mac):
+        arrs = [a.detach().to("cpu", torch.float64).contiguous()
+                for a in (alphas_cumprod, sqrt_recip, sqrt_recipm1, sqrt_ac, sqrt_1mac)]
+        check(self.handle, self.lib.d3dp_set_schedule(self.handle, *[ptr(a) for a in arrs], arrs[0].numel()),
+              "d3dp_set_schedule")
+
+    def alphas_cumprod(self):
+        out = torch.empty(self.num_timesteps, dtype=torch.float64)
+        check(self.handle, self.lib.d3dp_get_alphas_cumprod(self.handle, ptr(out), out.numel()), "get_alphas_cumprod")
+        return out
+
+    # ------------------------------------------------------------------ workspace
+    def workspace(self, B, H, flip):
+        n = C.c_size_t()
+        check(self.handle, self.lib.d3dp_workspace_bytes(self.handle, B, H, int(flip), C.byref(n)), "workspace_bytes")
+        if self._ws is None or self._ws.numel() < n.value:
+            self._ws = None
+            self._ws = torch.empty(n.value, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _f32(self, t):
+        return t.detach().to(self.device, torch.float32).contiguous()
+
+    # ------------------------------------------------------------------ entry points
+    def denoise(self, x2d, x_t, t):
+        x2d, x_t = self._f32(x2d), self._f32(x_t)
+        t = t.detach().to(self.device, torch.int64).contiguous()
+        B, H = x_t.shape[0], x_t.shape[1]
+        out = torch.empty_like(x_t)
+        ws = self.workspace(B, H, False)
+        with torch.cuda.device(self.device):
+            check(self.handle, self.lib.d3dp_denoise(self.handle, ptr(x2d), ptr(x_t), ptr(t), ptr(out), B, H, ptr(ws),
+                                                     ws.numel(), _stream()), "d3dp_denoise")
+        return out
+
+    def ddim_sample(self, x2d, x2d_flip, H, K, noise_init=None, noise_steps=None, seed=0, h_offset=0, H_total=None,
+                    timesteps=None):
+        x2d = self._f32(x2d)
+        x2d_flip = None if x2d_flip is None else self._f32(x2d_flip)
+        noise_init = None if noise_init is None else self._f32(noise_init)
+        noise_steps = None if noise_steps is None else self._f32(noise_steps)
+        B = x2d.shape[0]
+        H_total = H if H_total is None else H_total
+        preds = torch.empty(B, K, H, self.frames, 17, 3, dtype=torch.float32, device=self.device)
+        ws = self.workspace(B, H, x2d_flip is not None)
+        ts = None
+        if timesteps is not None:
+            ts = torch.tensor(list(timesteps), dtype=torch.int32)
+            assert ts.numel() == K + 1
+        with torch.cuda.device(self.device):
+            check(self.handle, self.lib.d3dp_ddim_sample(
+                self.handle, ptr(x2d), ptr(x2d_flip), ptr(noise_init), ptr(noise_steps), int(seed), int(h_offset),
+                int(H_total), ptr(ts), ptr(preds), B, H, K, ptr(ws), ws.numel(), _stream()), "d3dp_ddim_sample")
+        return preds
+
+    def q_sample(self, x0, noise, t, clamp=False):
+        x0, noise = self._f32(x0), self._f32(noise)
+        t = t.detach().to(self.device, torch.int64).contiguous()
+        B = x0.shape[0]
+        out = torch.empty_like(x0)
+        with torch.cuda.device(self.device):
+            check(self.handle, self.lib.d3dp_q_sample(self.handle, ptr(x0), ptr(noise), ptr(t), ptr(out), B,
+                                                      x0.numel() // B, int(clamp), _stream()), "d3dp_q_sample")
+        return out
+
+    def jpma(self, preds, traj, cam, x2d, root_joint=0, linear=False, return_e2d=False):
+        preds, traj, cam, x2d = self._f32(preds), self._f32(traj), self._f32(cam), self._f32(x2d)
+        B, K, H = preds.shape[0], preds.shape[1], preds.shape[2]
+        traj = traj.reshape(B, self.frames, 3)
+        if cam.dim() == 1:
+            cam = cam[None].expand(B, 9).contiguous()
+        jagg = torch.empty(B, K, self.frames, 17, 3, dtype=torch.float32, device=self.device)
+        pagg = torch.empty_like(jagg)
+        idx = torch.empty(B, K, self.frames, 17, dtype=torch.int32, device=self.device)
+        e2d = torch.empty(B, K, self.frames, 17, dtype=torch.float32, device=self.device) if return_e2d else None
+        with torch.cuda.device(self.device):
+            check(self.handle, self.lib.d3dp_jpma(self.handle, ptr(preds), ptr(traj), ptr(cam), ptr(x2d), ptr(jagg),
+                                                  ptr(idx), ptr(pagg), ptr(e2d), B, K, H, int(root_joint), int(linear),
+                                                  _stream()), "d3dp_jpma")
+        return (jagg, idx, pagg, e2d) if return_e2d else (jagg, idx, pagg)
+
+    def philox_normal(self, B, H, per_bh, seed, h_offset=0, H_total=None, draw=0):
+        out = torch.empty(B, H, per_bh, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.handle, self.lib.d3dp_philox_normal(self.handle, ptr(out), B, H, per_bh, int(seed), h_offset,
+                                                           H if H_total is None else H_total, draw, _stream()),
+                  "d3dp_philox_normal")
+        return out
+
+    # ------------------------------------------------------------------ kernel-level hooks (tests / profiling)
+    def test_gemm(self, mode, a16, w16, bias, x=None, ln_a=None, ln_b=None, tpos=None, F=1):
+        M, K = a16.shape
+        N = w16.shape[0]
+        out16 = torch.empty(M, N if mode < 2 else 512, dtype=torch.float16, device=self.device)
+        g_a, b_a, eps_a = ln_a if ln_a is not None else (None, None, 0.0)
+        g_b, b_b, eps_b = ln_b if ln_b is not None else (None, None, 0.0)
+        with torch.cuda.device(self.device):
+            check(self.handle, self.lib.d3dp_test_gemm(
+                self.handle, mode, ptr(a16), ptr(w16), ptr(bias), ptr(out16), ptr(x), ptr(g_a), ptr(b_a), eps_a,
+                ptr(g_b), ptr(b_b), eps_b, ptr(tpos), F, M, N, K, _stream()), "d3dp_test_gemm")
+        return out16
+
+    def test_attn(self, temporal, qkv16, n_streams):
+        T = qkv16.shape[0]
+        o16 = torch.zeros(T, 512, dtype=torch.float16, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.handle, self.lib.d3dp_test_attn(self.handle, int(temporal), ptr(qkv16), ptr(o16), n_streams,
+                                                       _stream()), "d3dp_test_attn")
+        return o16
