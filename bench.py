@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Benchmark of the D3DP diffusion-sampling hot path (BASELINE.json metric: poses/sec at H=20, K=10, F=243).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one full sampler call on one batch of synthetic clips: D3DP.ddim_sample_flip (2*K denoiser passes, flip
+TTA, DDIM updates) followed by the JPMA aggregation.  Workload at N=1 is BASELINE config "1xB200: F=243, H=20 K=10,
+batch=4".  With N>1 the hypothesis axis is sharded, 20 hypotheses per GPU (H_total = 20*N, config "8xB200: H=160
+sharded 20/GPU"): zero communication inside the sampler, one NCCL all-gather of the per-rank predictions, JPMA on
+every rank ("scaling": "weak").  Unit: one pose = one output frame aggregated over 20 hypotheses x 10 steps x 2
+flips, so value = B*F*(H_total/20) / seconds.
+
+Prints ONE JSON line (rank 0).  `value` has inputs resident in HBM; `e2e` goes through the public D3DP API with
+host (pinned) inputs and a device->host read of the aggregated poses inside the timed region.
+`--impl reference` times the reference's CPU PyTorch path (the oracle port, oracle/d3dp_oracle.py, all host threads)
+on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_FRAMES, B_CLIPS, H_PER_GPU, K_STEPS = 243, 4, 20, 10
+METRIC = "poses/sec (H=20,K=10,F=243)"
+C, J = 512, 17
+
+
+def f_tok(F):
+    """Algorithmic FLOPs per token per denoiser forward (SURVEY §8d / BASELINE.md §3)."""
+    return 256 * C * C + 8 * 4 * J * C + 8 * 4 * F * C + 10 * C + 6 * C
+
+
+def sampler_flops(B, H, K, F):
+    return f_tok(F) * B * H * F * J * K * 2
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops": d["bf16_tflops"], "tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "hbm_gbs": d["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if not (t0 <= ts <= t1 + 0.2):
+                continue
+            parts = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------- CPU reference
+def cpu_reference_sample(repeats, warmup=0):
+    """Time the oracle port of the reference's CPU PyTorch path on a bounded sample: one clip, one hypothesis, one
+    DDIM step at F=243 with flip TTA (2 denoiser forwards).  Cost is exactly linear in B*H*K, so
+    poses/s at (H=20,K=10) = F / (t_sample * 20 * 10)."""
+    import torch
+    from d3dp_b200.synthetic import (H36M_JOINTS_LEFT as JL, H36M_JOINTS_RIGHT as JR, synthetic_inputs,
+                                     synthetic_pose_estimator_state)
+    from oracle import d3dp_oracle as orc
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    sd = synthetic_pose_estimator_state(F_FRAMES, seed=0)
+    x2d, x2d_flip, n0, ns = synthetic_inputs(1, 1, 1, F_FRAMES)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + repeats):
+            t0 = time.perf_counter()
+            orc.ddim_sample(sd, x2d, x2d_flip, 1, 1, n0, ns, JL, JR)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    value = F_FRAMES / (t * H_PER_GPU * K_STEPS)
+    return value, t, cores
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    value, t, cores = cpu_reference_sample(args.steps, args.warmup)
+    sample = (f"oracle port of D3DP.ddim_sample_flip on CPU, B=1 H=1 K=1 F=243 (2 MixSTE2 forwards) per step, "
+              f"{t:.2f} s/step; scaled by B*H*K linearity to H=20,K=10")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "poses/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"F={F_FRAMES} J=17 C=512 B={B_CLIPS} H={H_PER_GPU} K={K_STEPS} flip-TTA (bounded sample)"},
+        "cpu_baseline": {"value": value, "unit": "poses/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------- our arm
+def kernel_rooflines(eng, T, n_streams, peaks):
+    """Time each hot kernel alone at the workload's shapes with CUDA events on the launching stream."""
+    import torch
+    dev = eng.device
+    g = torch.Generator(device="cpu").manual_seed(0)
+    a512 = (torch.randn(1024, 512, generator=g).half().repeat((T + 1023) // 1024, 1)[:T]).to(dev)
+    a1024 = torch.cat([a512, a512], dim=1)
+    bias = torch.zeros(1536, device=dev)
+    ones, zeros = torch.ones(512, device=dev), torch.zeros(512, device=dev)
+    x = torch.zeros(T, 512, device=dev)
+    res = {}
+
+    def timeit(fn, reps=8):
+        for _ in range(2):
+            fn()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s.record()
+        for _ in range(reps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / reps * 1e-3
+
+    def wmat(n, k):
+        return (torch.randn(n, k, generator=g) * 0.03).half().to(dev)
+
+    specs = [("gemm_qkv", 0, a512, wmat(1536, 512)), ("gemm_fc1_gelu", 1, a512, wmat(1024, 512)),
+             ("gemm_proj_res_ln", 2, a512, wmat(512, 512)), ("gemm_fc2_res_ln2", 3, a1024, wmat(512, 1024))]
+    for name, mode, a, w in specs:
+        kw = {}
+        if mode >= 2:
+            kw = dict(x=x, ln_a=(ones, zeros, 1e-6))
+        if mode == 3:
+            kw["ln_b"] = (ones, zeros, 1e-6)
+        t = timeit(lambda: eng.test_gemm(mode, a, w, bias, F=eng.frames, **kw))
+        fl = 2.0 * T * w.shape[0] * w.shape[1]
+        res[name] = {"ms": t * 1e3, "tflops": fl / t / 1e12, "frac_tensor": fl / t / 1e12 / peaks["tflops"]}
+    qkv = torch.cat([a512, a512, a512], dim=1).contiguous()
+    for name, temporal in (("attn_temporal", True), ("attn_spatial", False)):
+        t = timeit(lambda: eng.test_attn(temporal, qkv, n_streams))
+        L = eng.frames if temporal else J
+        fl = 4.0 * L * C * T  # QK^T + PV
+        byt = T * (1536 + 512) * 2.0
+        res[name] = {"ms": t * 1e3, "tflops": fl / t / 1e12, "frac_tensor": fl / t / 1e12 / peaks["tflops"],
+                     "gbs": byt / t / 1e9, "frac_hbm": byt / t / 1e9 / peaks["hbm_gbs"]}
+    return res
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from d3dp_b200 import D3DP
+    from d3dp_b200.synthetic import (H36M_JOINTS_LEFT as JL, H36M_JOINTS_RIGHT as JR, flip_2d, synthetic_camera,
+                                     synthetic_pose_estimator_state)
+    from d3dp_b200.distributed import gather_hypotheses
+    from tests.util import make_args  # tiny argparse-namespace helper
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    F, B, H, K = F_FRAMES, B_CLIPS, H_PER_GPU, K_STEPS
+    H_total = H * world
+    peaks = measured_peaks()
+
+    model = D3DP(make_args(F), JL, JR, is_train=False, num_proposals=H, sampling_timesteps=K)
+    model.pose_estimator.load_state_dict(synthetic_pose_estimator_state(F, seed=0), strict=True)
+    model = model.to(dev).eval()
+    eng = model.pose_estimator.engine()
+
+    g = torch.Generator().manual_seed(1234)
+    x2d_host = (0.3 * torch.randn(B, F, 17, 2, generator=g)).pin_memory()
+    x2d_flip_host = flip_2d(x2d_host).pin_memory()
+    traj_h, cam_h = synthetic_camera(B, F)
+    traj_host, cam_host = traj_h.pin_memory(), cam_h.pin_memory()
+    x2d, x2d_flip, traj, cam = x2d_host.to(dev), x2d_flip_host.to(dev), traj_host.to(dev), cam_host.to(dev)
+
+    def step(i, from_host=False):
+        if from_host:
+            a, b = x2d_host.to(dev, non_blocking=True), x2d_flip_host.to(dev, non_blocking=True)
+            tr, cm = traj_host.to(dev, non_blocking=True), cam_host.to(dev, non_blocking=True)
+        else:
+            a, b, tr, cm = x2d, x2d_flip, traj, cam
+        preds = model.ddim_sample_flip(a, None, input_2d_flip=b, seed=1000 + i, h_offset=rank * H, H_total=H_total)
+        preds = gather_hypotheses(preds, world)
+        jagg, idx, pagg = eng.jpma(preds, tr, cm, a)
+        if from_host:
+            return jagg.to("cpu", non_blocking=True), pagg.to("cpu", non_blocking=True)
+        return jagg, pagg
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, from_host):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(n):
+            step(i, from_host)
+        e.record()
+        barrier()
+        t = torch.tensor([s.elapsed_time(e) * 1e-3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    for i in range(args.warmup):
+        step(i)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    w0 = time.time()
+    t_total = timed(args.steps, False)
+    w1 = time.time()
+    clocks = sampler.stop(w0, w1) if sampler else None
+    step(0, True)  # warm the host path
+    t_e2e = timed(args.steps, True)
+
+    units = B * F * (H_total / 20.0) * args.steps
+    value, e2e_value = units / t_total, units / t_e2e
+    if rank != 0:
+        return
+    flops = sampler_flops(B, H_total, K, F) * args.steps
+    n_streams = 2 * B * H
+    T = n_streams * J * F
+    kern = kernel_rooflines(eng, T, n_streams, peaks)
+    # per-step launch counts of each kernel -> share of the step and the dominant one
+    per_step = {"gemm_qkv": 16 * K, "gemm_fc1_gelu": 16 * K, "gemm_proj_res_ln": 16 * K,
+                "gemm_fc2_res_ln2": 16 * K, "attn_temporal": 8 * K, "attn_spatial": 8 * K}
+    for k_, v in kern.items():
+        v["launches_per_step"] = per_step[k_]
+        v["share_of_step"] = v["ms"] * per_step[k_] / (t_total / args.steps * 1e3)
+    dom = max(kern, key=lambda k_: kern[k_]["share_of_step"])
+    dom_flops = {"gemm_qkv": 2.0 * T * 1536 * 512, "gemm_fc1_gelu": 2.0 * T * 1024 * 512,
+                 "gemm_proj_res_ln": 2.0 * T * 512 * 512, "gemm_fc2_res_ln2": 2.0 * T * 512 * 1024,
+                 "attn_temporal": 4.0 * F * C * T, "attn_spatial": 4.0 * J * C * T}[dom]
+    launches_per_call = K * (3 + 16 * 5 + 1 + 1) + 1 + 1  # fill_t,time_mlp,embed + 16 blocks x 5 + head + ddim; philox, jpma
+    cpu_line = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, t_s, cores = cpu_reference_sample(repeats=4, warmup=1)
+        cpu_line = {"value": v, "unit": "poses/s", "cores": cores, "kind": "port",
+                    "sample": f"oracle port, B=1 H=1 K=1 F=243 flip (2 forwards), {t_s:.2f} s each x4, "
+                              f"scaled by B*H*K linearity to H=20,K=10"}
+    h2d = (x2d_host.numel() + x2d_flip_host.numel() + traj_host.numel() + cam_host.numel()) * 4
+    d2h = 2 * B * K * F * 17 * 3 * 4
+    line = {
+        "metric": METRIC, "value": value, "unit": "poses/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp16 operands, fp32 accumulate/residual/LN/softmax",
+        "data": "synthetic",
+        "config": {"workload": f"c3: F={F} J=17 C=512 depth=8, B={B} clips, H={H}/GPU (H_total={H_total}), K={K}, "
+                               f"flip-TTA, Philox noise in-kernel, JPMA (J-Agg+P-Agg) included",
+                   "parallelism": f"hypothesis-sharded x{world}, one NCCL all-gather" if world > 1 else "single GPU",
+                   "l2": "activation working set 6.5 GB per step >> 126 MB L2 (no flush needed)",
+                   "unit_definition": "pose = one output frame at H=20,K=10: B*F*(H_total/20) per step"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": t_e2e / args.steps * 1e3,
+                "api": "D3DP.ddim_sample_flip + Engine.jpma from pinned host tensors, aggregated poses copied back"},
+        "gpu_launches": launches_per_call * args.steps,
+        "sampler_tflops": flops / t_total / 1e12 / world,
+        "sampler_frac_of_sustained_peak": flops / t_total / 1e12 / world / peaks["tflops_sustained"],
+        "roofline": {"kernel": dom, "bound": "tensor", "achieved": kern[dom]["tflops"], "peak": peaks["tflops"],
+                     "unit": "TFLOP/s", "frac": kern[dom]["tflops"] / peaks["tflops"], "traffic": None,
+                     "flops_per_launch": dom_flops, "peak_source": peaks["source"] + ", burst bf16"},
+        "kernels": kern,
+    }
+    if cpu_line:
+        line["cpu_baseline"] = cpu_line
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl")
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(512) time_mlp_kernel(const long long* __restri
   const float tv = static_cast<float>(t[b]);
   {
     const int i = tid & 255;
-    const float w = expf(static_cast<float>(i) * -(logf(10000.0f) / 255.0f));
+    const float w = expf(static_cast<float>(i) * static_cast<float>(-9.210340371976184 / 255.0));
     const float a = tv * w;
     emb[tid] = tid < 256 ? sinf(a) : cosf(a);
   }

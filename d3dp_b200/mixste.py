@@ -1,0 +1,96 @@
+"""`MixSTE2` with the reference's constructor, parameter names and forward signature (common/mixste.py:141-298), whose
+forward pass runs in the sm_100a kernels behind the C ABI instead of ATen.
+
+The module tree below only *holds* the parameters (so `.state_dict()`, `.load_state_dict(strict=True)`, `.cuda()`,
+`.parameters()` and `nn.DataParallel` behave exactly as with the reference); it is built in the reference's
+registration order so `torch.manual_seed(s)` + construction yields the same default initialisation.
+"""
+from functools import partial
+
+import torch
+import torch.nn as nn
+
+from .engine import Engine, H36M_JOINTS_LEFT, H36M_JOINTS_RIGHT
+
+
+class _Attention(nn.Module):  # parameter holder for common/mixste.py:46-61
+    def __init__(self, dim, qkv_bias=True):
+        super().__init__()
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _Mlp(nn.Module):  # parameter holder for common/mixste.py:24-35
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class _Block(nn.Module):  # parameter holder for common/mixste.py:84-111
+    def __init__(self, dim, mlp_ratio, qkv_bias, norm_layer):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = _Attention(dim, qkv_bias)
+        self.norm2 = norm_layer(dim)
+        self.mlp = _Mlp(dim, int(dim * mlp_ratio))
+
+
+class MixSTE2(nn.Module):
+    def __init__(self, num_frame=9, num_joints=17, in_chans=2, embed_dim_ratio=32, depth=4, num_heads=8, mlp_ratio=2.,
+                 qkv_bias=True, qk_scale=None, drop_rate=0., attn_drop_rate=0., drop_path_rate=0.2, norm_layer=None,
+                 is_train=True, joints_left=H36M_JOINTS_LEFT, joints_right=H36M_JOINTS_RIGHT, scale=1.0):
+        super().__init__()
+        if (num_joints, in_chans, embed_dim_ratio, num_heads, float(mlp_ratio), bool(qkv_bias), qk_scale) != \
+                (17, 2, 512, 8, 2.0, True, None):
+            raise ValueError("d3dp_b200 implements the D3DP configuration of MixSTE2 only: 17 joints, 2 input "
+                             "channels, embed_dim_ratio=512, 8 heads, mlp_ratio=2, qkv_bias=True, qk_scale=None")
+        if not 1 <= depth <= 8 or not 1 <= num_frame <= 256:
+            raise ValueError("d3dp_b200 supports depth 1..8 and 1..256 frames in this build")
+        norm_layer = norm_layer or partial(nn.LayerNorm, eps=1e-6)
+        C = embed_dim_ratio
+        self.is_train = is_train
+        self.num_frame, self.block_depth = num_frame, depth
+        self._joints_left, self._joints_right, self._scale = list(joints_left), list(joints_right), float(scale)
+        self.Spatial_patch_to_embedding = nn.Linear(in_chans + 3, C)
+        self.Spatial_pos_embed = nn.Parameter(torch.zeros(1, num_joints, C))
+        self.Temporal_pos_embed = nn.Parameter(torch.zeros(1, num_frame, C))
+        # indices 1 and 3 carry the two Linear layers, like the reference's Sequential(sinusoid, Linear, GELU, Linear)
+        self.time_mlp = nn.Sequential(nn.Identity(), nn.Linear(C, C * 2), nn.Identity(), nn.Linear(C * 2, C))
+        self.STEblocks = nn.ModuleList([_Block(C, mlp_ratio, qkv_bias, norm_layer) for _ in range(depth)])
+        self.TTEblocks = nn.ModuleList([_Block(C, mlp_ratio, qkv_bias, norm_layer) for _ in range(depth)])
+        self.Spatial_norm = norm_layer(C)
+        self.Temporal_norm = norm_layer(C)
+        self.head = nn.Sequential(nn.LayerNorm(C), nn.Linear(C, 3))
+        self._engines = {}  # device index -> (Engine, weights fingerprint); shared by DataParallel replicas
+
+    # ------------------------------------------------------------------ engine management
+    def _fingerprint(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def engine(self):
+        """The per-device Engine with this module's current weights uploaded (re-packed when any parameter changed)."""
+        p0 = self.Spatial_pos_embed
+        if p0.device.type != "cuda":
+            raise RuntimeError("d3dp_b200.MixSTE2 runs on CUDA (sm_100a) only: move the module with .cuda() first")
+        idx = p0.device.index if p0.device.index is not None else torch.cuda.current_device()
+        fp = self._fingerprint()
+        ent = self._engines.get(idx)
+        if ent is None or ent[1] != fp:
+            with torch.cuda.device(idx):
+                eng = ent[0] if ent is not None else Engine(
+                    self.num_frame, self._joints_left, self._joints_right, depth=self.block_depth, scale=self._scale)
+                eng.load_pose_estimator_state({k: v for k, v in self.state_dict().items()})
+            self._engines[idx] = (eng, fp)
+            ent = self._engines[idx]
+        return ent[0]
+
+    # ------------------------------------------------------------------ reference surface
+    @torch.no_grad()
+    def forward(self, x_2d, x_3d, t):
+        """common/mixste.py:278-298.  eval: x_2d [b,f,17,2], x_3d [b,h,f,17,3], t [b] -> [b,h,f,17,3];
+        train layout (is_train=True): x_3d [b,f,17,3] -> [b,f,17,3] (forward only, no stochastic depth)."""
+        eng = self.engine()
+        if self.is_train:
+            return eng.denoise(x_2d, x_3d[:, None], t)[:, 0]
+        return eng.denoise(x_2d, x_3d, t)
