@@ -105,17 +105,32 @@ def cpu_reference_sample(repeats, warmup=0):
     from d3dp_b200.synthetic import (H36M_JOINTS_LEFT as JL, H36M_JOINTS_RIGHT as JR, synthetic_inputs,
                                      synthetic_pose_estimator_state)
     from oracle import d3dp_oracle as orc
-    cores = os.cpu_count()
-    torch.set_num_threads(cores)
     sd = synthetic_pose_estimator_state(F_FRAMES, seed=0)
     x2d, x2d_flip, n0, ns = synthetic_inputs(1, 1, 1, F_FRAMES)
-    times = []
-    with torch.no_grad():
-        for i in range(warmup + repeats):
-            t0 = time.perf_counter()
+
+    def once():
+        t0 = time.perf_counter()
+        with torch.no_grad():
             orc.ddim_sample(sd, x2d, x2d_flip, 1, 1, n0, ns, JL, JR)
-            if i >= warmup:
-                times.append(time.perf_counter() - t0)
+        return time.perf_counter() - t0
+
+    # give the CPU path its best shot: eager PyTorch on many-core hosts is fastest well below the core count
+    # (oversubscribed tiny ops), so calibrate the intra-op thread count once and use the fastest
+    ncpu = os.cpu_count() or 1
+    best = None
+    for nt in sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16), min(ncpu, 8)}, reverse=True):
+        torch.set_num_threads(nt)
+        once()
+        t = once()
+        if best is None or t < best[0]:
+            best = (t, nt)
+    cores = best[1]
+    torch.set_num_threads(cores)
+    times = []
+    for i in range(warmup + repeats):
+        t = once()
+        if i >= warmup:
+            times.append(t)
     t = sum(times) / len(times)
     value = F_FRAMES / (t * H_PER_GPU * K_STEPS)
     return value, t, cores

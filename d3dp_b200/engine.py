@@ -169,7 +169,7 @@ class Engine:
 
     def test_attn(self, temporal, qkv16, n_streams):
         T = qkv16.shape[0]
-        o16 = torch.zeros(T, 512, dtype=torch.float16, device=self.device)
+        o16 = torch.empty(T, 512, dtype=torch.float16, device=self.device)
         with torch.cuda.device(self.device):
             check(self.handle, self.lib.d3dp_test_attn(self.handle, int(temporal), ptr(qkv16), ptr(o16), n_streams,
                                                        _stream()), "d3dp_test_attn")
