@@ -173,8 +173,8 @@ int set_smem_attr(d3dp_handle* h, KernelT k, int bytes) {
 }
 
 // kernel instantiations used by the pipeline
-constexpr int kStagesN256 = 4, kStagesN512 = 2;
-auto* const k_gemm_qkv = gemm_tcgen05_kernel<256, EPI_BIAS_F16, kStagesN256, 4>;
+constexpr int kStagesN256 = 3, kStagesN512 = 2;
+auto* const k_gemm_qkv = gemm_tcgen05_kernel<256, EPI_BIAS_F16, kStagesN256, 8>;
 auto* const k_gemm_fc1 = gemm_tcgen05_kernel<256, EPI_BIAS_GELU_F16, kStagesN256, 8>;
 auto* const k_gemm_proj = gemm_tcgen05_kernel<512, EPI_RES_LN, kStagesN512, 8>;
 auto* const k_gemm_fc2 = gemm_tcgen05_kernel<512, EPI_RES_LN2, kStagesN512, 8>;
@@ -196,16 +196,21 @@ int ensure_attrs(d3dp_handle* h) {
 
 int launch_gemm(d3dp_handle* h, int mode, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                 cudaStream_t st) {
+  CUtensorMap tmC = tmA;  // F16 modes: output tensor map (TMA store); LN modes: unused
+  if (mode == EPI_BIAS_F16 || mode == EPI_BIAS_GELU_F16) {
+    int rc = make_tmap(h, &tmC, p.out16, p.M, p.ldo, 128);
+    if (rc) return rc;
+  }
   const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int bn = (mode == EPI_BIAS_F16 || mode == EPI_BIAS_GELU_F16) ? 256 : 512;
   if (p.N % bn != 0 || p.K % GEMM_BK != 0 || p.M <= 0) return fail(h, D3DP_E_INVALID, "gemm: unsupported shape");
   const int tiles = tiles_m * (p.N / bn);
   const int grid = tiles < h->num_sms ? tiles : h->num_sms;
   switch (mode) {
-    case EPI_BIAS_F16: k_gemm_qkv<<<grid, 64 + 4 * 32, kSmemN256, st>>>(tmA, tmB, p); break;
-    case EPI_BIAS_GELU_F16: k_gemm_fc1<<<grid, 64 + 8 * 32, kSmemN256, st>>>(tmA, tmB, p); break;
-    case EPI_RES_LN: k_gemm_proj<<<grid, 64 + 8 * 32, kSmemN512, st>>>(tmA, tmB, p); break;
-    case EPI_RES_LN2: k_gemm_fc2<<<grid, 64 + 8 * 32, kSmemN512, st>>>(tmA, tmB, p); break;
+    case EPI_BIAS_F16: k_gemm_qkv<<<grid, 64 + 8 * 32, kSmemN256, st>>>(tmA, tmB, tmC, p); break;
+    case EPI_BIAS_GELU_F16: k_gemm_fc1<<<grid, 64 + 8 * 32, kSmemN256, st>>>(tmA, tmB, tmC, p); break;
+    case EPI_RES_LN: k_gemm_proj<<<grid, 64 + 8 * 32, kSmemN512, st>>>(tmA, tmB, tmC, p); break;
+    case EPI_RES_LN2: k_gemm_fc2<<<grid, 64 + 8 * 32, kSmemN512, st>>>(tmA, tmB, tmC, p); break;
     default: return fail(h, D3DP_E_INVALID, "gemm: bad mode");
   }
   CK(cudaGetLastError());

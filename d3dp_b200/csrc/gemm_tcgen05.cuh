@@ -46,15 +46,36 @@ struct GemmSmem {
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr, LN exchange [2][2][128] floats
   static constexpr int RED_OFFSET = BAR_OFFSET + 256;
-  static constexpr int TOTAL = RED_OFFSET + 2 * 2 * 128 * 4 + 1024 /*alignment slack*/;
+  // per-launch column parameters staged once in smem (uniform LDS.128 broadcasts in the epilogue):
+  // [0,2560) bias (N <= 2560) ; LN modes: [512,1024) gamma_a [1024,1536) beta_a [1536,2048) gamma_b [2048,2560) beta_b
+  static constexpr int PARAM_OFFSET = RED_OFFSET + 2 * 2 * 128 * 4;
+  static constexpr int PARAM_FLOATS = 2560;
+  // BN=256 kernels: fp16 output staged per epilogue group in two 128x64 (16 KB, 128B-swizzled) slabs for TMA stores
+  static constexpr int OUT_OFFSET = (PARAM_OFFSET + PARAM_FLOATS * 4 + 1023) / 1024 * 1024;
+  static constexpr int OUT_BYTES = (BN == 256) ? 2 * 2 * 16384 : 0;
+  static constexpr int TOTAL = OUT_OFFSET + OUT_BYTES + 1024 /*alignment slack*/;
 };
 
-__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
+// erf by Abramowitz & Stegun 7.1.26 (|abs error| <= 1.5e-7): branch-free, 2 MUFU + 7 FMA, so the fc1 epilogue
+// keeps up with the MMA pipe.  The result feeds an fp16 store (rel. 4.9e-4), so this is exact-erf GELU for all
+// practical purposes (reference: nn.GELU() default = erf form, common/mixste.py:24,39).
+__device__ __forceinline__ float erf_as(float x) {
+  const float ax = fabsf(x);
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float r = fmaf(-poly, __expf(-ax * ax), 1.0f);
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erf_as(v * 0.70710678118654752f)); }
 
 template <int BN, int EPI, int STAGES, int EPI_WARPS>
 __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   using L = GemmSmem<BN, STAGES>;
   constexpr int ACC_STAGES = 512 / BN;
   constexpr int NSPLIT = EPI_WARPS / 4;   // threads sharing one row in the epilogue
@@ -71,6 +92,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* red = reinterpret_cast<float*>(smem + L::RED_OFFSET);  // [2 (buf)][NSPLIT][128]
+  float* sprm = reinterpret_cast<float*>(smem + L::PARAM_OFFSET);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -82,6 +104,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (BN == 256) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -93,6 +116,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  if constexpr (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16) {
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) sprm[i] = p.bias[i];
+  } else {
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+      sprm[i] = p.bias[i];
+      sprm[512 + i] = p.ln_a_g[i];
+      sprm[1024 + i] = p.ln_a_b[i];
+      if (EPI == EPI_RES_LN2 && p.ln_b_g != nullptr) {
+        sprm[1536 + i] = p.ln_b_g[i];
+        sprm[2048 + i] = p.ln_b_b[i];
+      }
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -167,28 +203,47 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + col0;
 
       if constexpr (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16) {
+        // Each 4-warp group owns COLS_PER_THREAD columns = slabs of 64 columns; a slab is staged in smem in the
+        // 128B-swizzled layout (conflict-free for one-row-per-thread 16 B writes) and written out by one TMA store.
+        static_assert(COLS_PER_THREAD % 64 == 0, "slab");
         const int n0 = n_blk * BN + col0;
-        __half* orow = p.out16 + static_cast<size_t>(g) * p.ldo + n0;
+        uint8_t* gbuf = smem + L::OUT_OFFSET + split * 2 * 16384;
+        const bool leader = (ew & 3) == 0 && lane == 0;
 #pragma unroll 1
-        for (int c = 0; c < COLS_PER_THREAD / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
-          uint32_t o[16];
+        for (int sl = 0; sl < COLS_PER_THREAD / 64; ++sl) {
+          uint8_t* buf = gbuf + (sl & 1) * 16384;
+          if (leader) tma_store_wait_read<1>();  // the store that last used this buffer has drained
+          named_bar_sync(2 + split, 128);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float a = __uint_as_float(v[2 * i]) + __ldg(p.bias + n0 + c * 32 + 2 * i);
-            float b = __uint_as_float(v[2 * i + 1]) + __ldg(p.bias + n0 + c * 32 + 2 * i + 1);
-            if constexpr (EPI == EPI_BIAS_GELU_F16) {
-              a = gelu_erf(a);
-              b = gelu_erf(b);
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = sl * 2 + cc;
+            uint32_t v[32];
+            tmem_ld32(taddr + c * 32, v);
+            tmem_ld_wait();
+            uint32_t o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 bb = *reinterpret_cast<const float2*>(sprm + n0 + c * 32 + 2 * i);
+              float a = __uint_as_float(v[2 * i]) + bb.x;
+              float b = __uint_as_float(v[2 * i + 1]) + bb.y;
+              if constexpr (EPI == EPI_BIAS_GELU_F16) {
+                a = gelu_erf(a);
+                b = gelu_erf(b);
+              }
+              o[i] = pack_half2(a, b);
             }
-            o[i] = pack_half2(a, b);
-          }
-          if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            for (int i = 0; i < 4; ++i) {
+              const int piece = cc * 4 + i;  // 16-byte piece index inside the 128-byte slab row
+              *reinterpret_cast<uint4*>(buf + r * 128 + ((piece ^ (r & 7)) << 4)) =
+                  make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(2 + split, 128);
+          if (leader) {
+            tma_store_2d(&tmC, buf, n0 + sl * 64, m_blk * GEMM_BM);
+            tma_store_commit();
           }
         }
       } else {
@@ -212,7 +267,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         };
         // pass 1: v = acc + bias + residual ; keep v in TMEM ; row sum
         float sum = 0.f;
-#pragma unroll 1
+#pragma unroll 2
         for (int c = 0; c < NCH; ++c) {
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
@@ -231,7 +286,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            float t = __uint_as_float(v[i]) + __ldg(p.bias + col0 + c * 32 + i) + res[i];
+            float t = __uint_as_float(v[i]) + sprm[col0 + c * 32 + i] + res[i];
             sum += t;
             v[i] = __float_as_uint(t);
           }
@@ -272,7 +327,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int n = col0 + c * 32;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            float y = (__uint_as_float(v[i]) - mean) * rstd * __ldg(p.ln_a_g + n + i) + __ldg(p.ln_a_b + n + i);
+            float y = (__uint_as_float(v[i]) - mean) * rstd * sprm[512 + n + i] + sprm[1024 + n + i];
             if constexpr (EPI == EPI_RES_LN2) {
               if (p.tpos) y += __ldg(p.tpos + static_cast<size_t>(f) * 512 + n + i);
               sum2 += y;
@@ -326,10 +381,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               uint32_t o[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                float a = (__uint_as_float(v[2 * i]) - mean2) * rstd2 * __ldg(p.ln_b_g + n + 2 * i) +
-                          __ldg(p.ln_b_b + n + 2 * i);
-                float b = (__uint_as_float(v[2 * i + 1]) - mean2) * rstd2 * __ldg(p.ln_b_g + n + 2 * i + 1) +
-                          __ldg(p.ln_b_b + n + 2 * i + 1);
+                float a = (__uint_as_float(v[2 * i]) - mean2) * rstd2 * sprm[1536 + n + 2 * i] + sprm[2048 + n + 2 * i];
+                float b = (__uint_as_float(v[2 * i + 1]) - mean2) * rstd2 * sprm[1536 + n + 2 * i + 1] +
+                          sprm[2048 + n + 2 * i + 1];
                 o[i] = pack_half2(a, b);
               }
               if (valid) {
@@ -349,6 +403,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   }
 
+  if (BN == 256) tma_store_wait_all<0>();  // no-op for threads that issued no bulk stores
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
