@@ -167,8 +167,8 @@ def kernel_rooflines(eng, T, n_streams, peaks):
     x = torch.zeros(T, 512, device=dev)
     res = {}
 
-    def timeit(fn, reps=8):
-        for _ in range(2):
+    def timeit(fn, reps=int(os.environ.get("D3DP_PROFILE_REPS", 8))):
+        for _ in range(min(2, reps)):
             fn()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()

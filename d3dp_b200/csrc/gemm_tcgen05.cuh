@@ -273,11 +273,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_ld32(taddr + c * 32, v);
           float res[32];
           if (valid) {
-            const float4* src = reinterpret_cast<const float4*>(xrow + c * 32);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 t = src[i];
-              res[4 * i] = t.x; res[4 * i + 1] = t.y; res[4 * i + 2] = t.z; res[4 * i + 3] = t.w;
+            for (int i = 0; i < 4; ++i) {
+              uint32_t t[8];
+              ldg256(xrow + c * 32 + 8 * i, t);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) res[8 * i + q] = __uint_as_float(t[q]);
             }
           } else {
 #pragma unroll
@@ -293,11 +294,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_st32(taddr + c * 32, v);
           if constexpr (EPI == EPI_RES_LN) {
             if (valid) {
-              float4* dst = reinterpret_cast<float4*>(xrow + c * 32);
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                     __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+              for (int i = 0; i < 4; ++i)
+                stg256(xrow + c * 32 + 8 * i, v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3], v[8 * i + 4],
+                       v[8 * i + 5], v[8 * i + 6], v[8 * i + 7]);
             }
           }
         }
@@ -336,22 +336,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           if constexpr (EPI == EPI_RES_LN) {
             if (valid) {
-              uint4* dst = reinterpret_cast<uint4*>(arow + c * 32);
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                dst[i] = make_uint4(pack_half2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
-                                    pack_half2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
-                                    pack_half2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
-                                    pack_half2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
+              for (int i = 0; i < 2; ++i)
+                stg256(arow + c * 32 + 16 * i,
+                       pack_half2(__uint_as_float(v[16 * i]), __uint_as_float(v[16 * i + 1])),
+                       pack_half2(__uint_as_float(v[16 * i + 2]), __uint_as_float(v[16 * i + 3])),
+                       pack_half2(__uint_as_float(v[16 * i + 4]), __uint_as_float(v[16 * i + 5])),
+                       pack_half2(__uint_as_float(v[16 * i + 6]), __uint_as_float(v[16 * i + 7])),
+                       pack_half2(__uint_as_float(v[16 * i + 8]), __uint_as_float(v[16 * i + 9])),
+                       pack_half2(__uint_as_float(v[16 * i + 10]), __uint_as_float(v[16 * i + 11])),
+                       pack_half2(__uint_as_float(v[16 * i + 12]), __uint_as_float(v[16 * i + 13])),
+                       pack_half2(__uint_as_float(v[16 * i + 14]), __uint_as_float(v[16 * i + 15])));
             }
           } else {
             tmem_st32(taddr + c * 32, v);
             if (valid) {
-              float4* dst = reinterpret_cast<float4*>(xrow + c * 32);
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                     __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+              for (int i = 0; i < 4; ++i)
+                stg256(xrow + c * 32 + 8 * i, v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3], v[8 * i + 4],
+                       v[8 * i + 5], v[8 * i + 6], v[8 * i + 7]);
             }
           }
         }
@@ -387,9 +390,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 o[i] = pack_half2(a, b);
               }
               if (valid) {
-                uint4* dst = reinterpret_cast<uint4*>(arow + c * 32);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                for (int i = 0; i < 2; ++i)
+                  stg256(arow + c * 32 + 16 * i, o[8 * i], o[8 * i + 1], o[8 * i + 2], o[8 * i + 3], o[8 * i + 4],
+                         o[8 * i + 5], o[8 * i + 6], o[8 * i + 7]);
               }
             }
           }

@@ -88,6 +88,19 @@ __device__ __forceinline__ void tma_store_wait_all() {
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// 256-bit global accesses (LDG.256 / STG.256, sm_100+): one full 32-byte sector per lane, which matters for the
+// one-row-per-thread epilogues where every lane touches a different cache line
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,
+                                       uint32_t f, uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e),
+               "r"(f), "r"(g), "r"(h)
+               : "memory");
+}
 // approximate reciprocal (MUFU.RCP), ~1 ulp
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
