@@ -15,6 +15,7 @@
 #include "attn_spatial.cuh"
 #include "attn_temporal.cuh"
 #include "elementwise.cuh"
+#include "gemm_ln_pair.cuh"
 #include "gemm_tcgen05.cuh"
 
 using namespace d3dp;
@@ -72,13 +73,16 @@ int fail(d3dp_handle* h, int code, const std::string& msg) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// 2-D fp16 row-major tensor map, 128-byte swizzle, box = {64 columns, box_rows}
-int make_tmap(d3dp_handle* h, CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// 2-D row-major tensor map, 128-byte swizzle, box = {128 bytes of columns, box_rows}; fp16 (default) or fp32
+int make_tmap(d3dp_handle* h, CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
+              bool f32 = false) {
+  const uint32_t esz = f32 ? 4 : 2;
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {cols * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t gstride[1] = {cols * esz};
+  cuuint32_t box[2] = {128 / esz, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  CUresult r = h->encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                         const_cast<void*>(ptr), gdim, gstride, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -173,13 +177,14 @@ int set_smem_attr(d3dp_handle* h, KernelT k, int bytes) {
 }
 
 // kernel instantiations used by the pipeline
-constexpr int kStagesN256 = 3, kStagesN512 = 2;
+constexpr int kStagesN256 = 3;
 auto* const k_gemm_qkv = gemm_tcgen05_kernel<256, EPI_BIAS_F16, kStagesN256, 8>;
 auto* const k_gemm_fc1 = gemm_tcgen05_kernel<256, EPI_BIAS_GELU_F16, kStagesN256, 8>;
-auto* const k_gemm_proj = gemm_tcgen05_kernel<512, EPI_RES_LN, kStagesN512, 8>;
-auto* const k_gemm_fc2 = gemm_tcgen05_kernel<512, EPI_RES_LN2, kStagesN512, 8>;
+constexpr int kLnStages = 3, kLnRing = 2;
+auto* const k_gemm_proj = gemm_ln_pair_kernel<EPI_RES_LN, kLnStages, kLnRing>;
+auto* const k_gemm_fc2 = gemm_ln_pair_kernel<EPI_RES_LN2, kLnStages, kLnRing>;
 constexpr int kSmemN256 = GemmSmem<256, kStagesN256>::TOTAL;
-constexpr int kSmemN512 = GemmSmem<512, kStagesN512>::TOTAL;
+constexpr int kSmemN512 = LnPairSmem<kLnStages, kLnRing>::TOTAL;
 
 int ensure_attrs(d3dp_handle* h) {
   if (h->attrs_set) return D3DP_OK;
@@ -196,9 +201,12 @@ int ensure_attrs(d3dp_handle* h) {
 
 int launch_gemm(d3dp_handle* h, int mode, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                 cudaStream_t st) {
-  CUtensorMap tmC = tmA;  // F16 modes: output tensor map (TMA store); LN modes: unused
+  CUtensorMap tmC = tmA;  // F16 modes: output tensor map (TMA store); LN modes: residual stream x (TMA load)
   if (mode == EPI_BIAS_F16 || mode == EPI_BIAS_GELU_F16) {
     int rc = make_tmap(h, &tmC, p.out16, p.M, p.ldo, 128);
+    if (rc) return rc;
+  } else {
+    int rc = make_tmap(h, &tmC, p.x, p.M, 512, 128, /*f32=*/true);
     if (rc) return rc;
   }
   const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
@@ -209,8 +217,13 @@ int launch_gemm(d3dp_handle* h, int mode, const CUtensorMap& tmA, const CUtensor
   switch (mode) {
     case EPI_BIAS_F16: k_gemm_qkv<<<grid, 64 + 8 * 32, kSmemN256, st>>>(tmA, tmB, tmC, p); break;
     case EPI_BIAS_GELU_F16: k_gemm_fc1<<<grid, 64 + 8 * 32, kSmemN256, st>>>(tmA, tmB, tmC, p); break;
-    case EPI_RES_LN: k_gemm_proj<<<grid, 64 + 8 * 32, kSmemN512, st>>>(tmA, tmB, tmC, p); break;
-    case EPI_RES_LN2: k_gemm_fc2<<<grid, 64 + 8 * 32, kSmemN512, st>>>(tmA, tmB, tmC, p); break;
+    case EPI_RES_LN:
+    case EPI_RES_LN2: {
+      const int pairs = tiles_m < h->num_sms / 2 ? tiles_m : h->num_sms / 2;  // one CTA pair (cluster) per M tile
+      if (mode == EPI_RES_LN) k_gemm_proj<<<2 * pairs, 352, kSmemN512, st>>>(tmA, tmB, tmC, p);
+      else k_gemm_fc2<<<2 * pairs, 352, kSmemN512, st>>>(tmA, tmB, tmC, p);
+      break;
+    }
     default: return fail(h, D3DP_E_INVALID, "gemm: bad mode");
   }
   CK(cudaGetLastError());

@@ -1,0 +1,367 @@
+// Residual + LayerNorm GEMMs (attn.proj and mlp.fc2 of every MixSTE block; reference: common/mixste.py:80,41 with the
+// residual adds of Block.forward :114-115 and the LayerNorms that follow, :114,115,243,257,269,273) as a
+// 2-CTA-cluster kernel.
+//
+// A LayerNorm needs whole 512-wide rows, and a 128x512 fp32 accumulator is all 512 TMEM columns of an SM, which
+// would serialise MMA and epilogue.  Here a CTA pair shares each 128-row tile: CTA `rank` computes columns
+// [256*rank, 256*rank+256), so each SM holds two 256-column accumulator stages and the epilogue of tile i overlaps
+// the MMAs of tile i+1.  Row statistics are combined across the four 128-column quarters (2 epilogue groups x 2
+// CTAs) with Chan's parallel mean/M2 formula: every thread owns one row-quarter, publishes (mean, M2) to both CTAs'
+// shared memory (st.shared::cluster) and the exchange is closed by an mbarrier that counts warps of both CTAs.
+// The residual tile is streamed by TMA into a small swizzled ring (no uncoalesced row-per-thread global loads);
+// outputs leave with 256-bit stores, one full 32 B sector per lane.
+//
+//   EPI_RES_LN   x += A.W^T + b ; a16 = fp16(LN_a(x))
+//   EPI_RES_LN2  v = x + A.W^T + b ; x = LN_a(v) (+Tpos[f]) ; a16 = fp16(LN_b(x))   (LN_b optional)
+#pragma once
+#include "gemm_tcgen05.cuh"
+
+namespace d3dp {
+
+template <int STAGES, int RING>
+struct LnPairSmem {
+  static constexpr int A_BYTES = 128 * 64 * 2;
+  static constexpr int B_BYTES = 256 * 64 * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;             // 48 KB
+  static constexpr int RING_OFFSET = STAGES * STAGE_BYTES;          // [2 groups][RING] x 16 KB residual chunks
+  static constexpr int SLOT_BYTES = 128 * 32 * 4;
+  static constexpr int BAR_OFFSET = RING_OFFSET + 2 * RING * SLOT_BYTES;
+  // barriers: full[STAGES] empty[STAGES] tfull[2] tempty[2] rfull[2][RING] rempty[2][RING] xch[2] ; tmem ptr
+  static constexpr int XCH_OFFSET = BAR_OFFSET + 512;               // [2 bufs][4 quarters][128 rows] float2
+  static constexpr int PARAM_OFFSET = XCH_OFFSET + 2 * 4 * 128 * 8; // 5 x 256 floats: bias, g_a, b_a, g_b, b_b
+  static constexpr int TOTAL = PARAM_OFFSET + 5 * 256 * 4 + 1024;
+};
+
+template <int EPI, int STAGES, int RING>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1)
+gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
+  using L = LnPairSmem<STAGES, RING>;
+  static_assert(EPI == EPI_RES_LN || EPI == EPI_RES_LN2, "LN epilogues only");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* rfull_bar = tempty_bar + 2;          // [g*RING + slot]
+  uint64_t* rempty_bar = rfull_bar + 2 * RING;
+  uint64_t* xch_bar = rempty_bar + 2 * RING;     // [buf]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(xch_bar + 2);
+  float2* xch = reinterpret_cast<float2*>(smem + L::XCH_OFFSET);
+  float* sprm = reinterpret_cast<float*>(smem + L::PARAM_OFFSET);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int tiles_m = (p.M + 127) / 128;
+  const int KB = p.K / 64;
+  const int ncol0 = rank * 256;  // first global column of this CTA's half
+  const bool has_b = (EPI == EPI_RES_LN2) && p.ln_b_g != nullptr;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 8);
+      mbar_init(&xch_bar[a], 16);  // 8 epilogue warps of each CTA of the pair
+    }
+    for (int i = 0; i < 2 * RING; ++i) {
+      mbar_init(&rfull_bar[i], 1);
+      mbar_init(&rempty_bar[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    sprm[i] = p.bias[ncol0 + i];
+    sprm[256 + i] = p.ln_a_g[ncol0 + i];
+    sprm[512 + i] = p.ln_a_b[ncol0 + i];
+    if (has_b) {
+      sprm[768 + i] = p.ln_b_g[ncol0 + i];
+      sprm[1024 + i] = p.ln_b_b[ncol0 + i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // peer's barriers are initialised before anyone arrives remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ operand TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = cluster_id; tile < tiles_m; tile += num_clusters) {
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[s], kb * 64, tile * 128);
+          tma_load_2d(sa + L::A_BYTES, &tmB, &full_bar[s], kb * 64, ncol0);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, 256, 0, 0);
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int tile = cluster_id; tile < tiles_m; tile += num_clusters) {
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 256;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t b_base = a_base + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_f16_ss(d_tmem, make_sdesc_sw128(a_base + k * 32, 16, 1024), make_sdesc_sw128(b_base + k * 32, 16, 1024),
+                       idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        tc_commit(&tfull_bar[as]);
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ residual TMA loader (x tile, 32-col chunks)
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t ph = 0;
+      for (int tile = cluster_id; tile < tiles_m; tile += num_clusters) {
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const int bi = g * RING + slot;
+            mbar_wait(&rempty_bar[bi], ph ^ 1);
+            mbar_expect_tx(&rfull_bar[bi], L::SLOT_BYTES);
+            tma_load_2d(smem + L::RING_OFFSET + bi * L::SLOT_BYTES, &tmX, &rfull_bar[bi],
+                        ncol0 + g * 128 + c * 32, tile * 128);
+          }
+          if (++slot == RING) { slot = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: 2 groups x 4 warps
+    const int ew = warp - 3;
+    const int g = ew >> 2;            // column group: local columns [128g, 128g+128)
+    const int quad = warp & 3;        // TMEM lane quadrant of this warp
+    const int r = quad * 32 + lane;   // tile row == TMEM lane
+    const int lcol0 = g * 128;        // first local column
+    const int qd = rank * 2 + g;      // quarter index of this thread's columns within the 512-wide row
+    const uint32_t peer = rank ^ 1u;
+    const uint32_t xch_local = smem_u32(xch);
+    const uint32_t xch_remote = mapa_u32(xch_local, peer);
+    const uint32_t xbar_remote0 = mapa_u32(smem_u32(&xch_bar[0]), peer);
+    int as = 0, rslot = 0, xn = 0;
+    uint32_t aph = 0, rph = 0;
+
+    // publish this row-quarter's (mean, M2), wait for all four quarters, return the row's mean and rstd
+    auto exchange = [&](float m_loc, float m2_loc, float eps, float& mean, float& rstd) {
+      const int buf = xn & 1;
+      const uint32_t off = static_cast<uint32_t>(((buf * 4 + qd) * 128 + r) * 8);
+      xch[(buf * 4 + qd) * 128 + r] = make_float2(m_loc, m2_loc);
+      st_cluster_f32x2(xch_remote + off, m_loc, m2_loc);
+      fence_acq_rel_cluster();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_cluster(smem_u32(&xch_bar[buf]));            // own CTA
+        mbar_arrive_cluster(xbar_remote0 + buf * 8);             // peer CTA
+      }
+      mbar_wait_cluster(&xch_bar[buf], (xn >> 1) & 1);
+      float ms[4], m2s[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 t = xch[(buf * 4 + q) * 128 + r];
+        ms[q] = t.x;
+        m2s[q] = t.y;
+      }
+      mean = 0.25f * ((ms[0] + ms[1]) + (ms[2] + ms[3]));
+      float m2 = (m2s[0] + m2s[1]) + (m2s[2] + m2s[3]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) m2 = fmaf(128.0f * (ms[q] - mean), ms[q] - mean, m2);
+      rstd = rsqrtf(m2 * (1.0f / 512.0f) + eps);
+      ++xn;
+    };
+
+    for (int tile = cluster_id; tile < tiles_m; tile += num_clusters) {
+      const int grow = tile * 128 + r;
+      const bool valid = grow < p.M;
+      float* xrow = p.x + static_cast<size_t>(grow) * 512 + ncol0 + lcol0;
+      __half* arow = p.out16 ? p.out16 + static_cast<size_t>(grow) * 512 + ncol0 + lcol0 : nullptr;
+      const int f = valid ? (grow % p.F) : 0;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256 + lcol0;
+
+      // ---- pass 1: v = acc + bias + residual -> TMEM ; row-quarter sum
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        const int bi = g * RING + rslot;
+        mbar_wait(&rfull_bar[bi], rph);
+        const uint8_t* slot = smem + L::RING_OFFSET + bi * L::SLOT_BYTES + r * 128;
+        float res[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = *reinterpret_cast<const float4*>(slot + ((j ^ (r & 7)) << 4));
+          res[4 * j] = t.x; res[4 * j + 1] = t.y; res[4 * j + 2] = t.z; res[4 * j + 3] = t.w;
+        }
+        // generic-proxy reads of the slot must be ordered before the TMA (async proxy) refill
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rempty_bar[bi]);
+        if (++rslot == RING) { rslot = 0; rph ^= 1; }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float t = __uint_as_float(v[i]) + sprm[lcol0 + c * 32 + i] + res[i];
+          sum += t;
+          v[i] = __float_as_uint(t);
+        }
+        tmem_st32(taddr + c * 32, v);
+        if constexpr (EPI == EPI_RES_LN) {
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              stg256(xrow + c * 32 + 8 * i, v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3], v[8 * i + 4],
+                     v[8 * i + 5], v[8 * i + 6], v[8 * i + 7]);
+          }
+        }
+      }
+      tmem_st_wait();
+      const float m_loc = sum * (1.0f / 128.0f);
+      // ---- pass 2: M2 about the local mean
+      float m2_loc = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float d = __uint_as_float(v[i]) - m_loc;
+          m2_loc = fmaf(d, d, m2_loc);
+        }
+      }
+      float mean, rstd;
+      exchange(m_loc, m2_loc, p.ln_a_eps, mean, rstd);
+      // ---- pass 3: y = LN_a(v)
+      float sum2 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+        const int n = lcol0 + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float y = (__uint_as_float(v[i]) - mean) * rstd * sprm[256 + n + i] + sprm[512 + n + i];
+          if constexpr (EPI == EPI_RES_LN2) {
+            if (p.tpos) y += __ldg(p.tpos + static_cast<size_t>(f) * 512 + ncol0 + n + i);
+            sum2 += y;
+          }
+          v[i] = __float_as_uint(y);
+        }
+        if constexpr (EPI == EPI_RES_LN) {
+          if (valid && arow) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              stg256(arow + c * 32 + 16 * i,
+                     pack_half2(__uint_as_float(v[16 * i]), __uint_as_float(v[16 * i + 1])),
+                     pack_half2(__uint_as_float(v[16 * i + 2]), __uint_as_float(v[16 * i + 3])),
+                     pack_half2(__uint_as_float(v[16 * i + 4]), __uint_as_float(v[16 * i + 5])),
+                     pack_half2(__uint_as_float(v[16 * i + 6]), __uint_as_float(v[16 * i + 7])),
+                     pack_half2(__uint_as_float(v[16 * i + 8]), __uint_as_float(v[16 * i + 9])),
+                     pack_half2(__uint_as_float(v[16 * i + 10]), __uint_as_float(v[16 * i + 11])),
+                     pack_half2(__uint_as_float(v[16 * i + 12]), __uint_as_float(v[16 * i + 13])),
+                     pack_half2(__uint_as_float(v[16 * i + 14]), __uint_as_float(v[16 * i + 15])));
+          }
+        } else {
+          if (has_b) tmem_st32(taddr + c * 32, v);
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              stg256(xrow + c * 32 + 8 * i, v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3], v[8 * i + 4],
+                     v[8 * i + 5], v[8 * i + 6], v[8 * i + 7]);
+          }
+        }
+      }
+      if constexpr (EPI == EPI_RES_LN2) {
+        if (has_b) {  // uniform over the grid
+          tmem_st_wait();
+          const float m_loc2 = sum2 * (1.0f / 128.0f);
+          float m2_loc2 = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float d = __uint_as_float(v[i]) - m_loc2;
+              m2_loc2 = fmaf(d, d, m2_loc2);
+            }
+          }
+          float mean2, rstd2;
+          exchange(m_loc2, m2_loc2, p.ln_b_eps, mean2, rstd2);
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c * 32, v);
+            tmem_ld_wait();
+            const int n = lcol0 + c * 32;
+            uint32_t o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float a = (__uint_as_float(v[2 * i]) - mean2) * rstd2 * sprm[768 + n + 2 * i] + sprm[1024 + n + 2 * i];
+              const float b = (__uint_as_float(v[2 * i + 1]) - mean2) * rstd2 * sprm[768 + n + 2 * i + 1] +
+                              sprm[1024 + n + 2 * i + 1];
+              o[i] = pack_half2(a, b);
+            }
+            if (valid && arow) {
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+                stg256(arow + c * 32 + 16 * i, o[8 * i], o[8 * i + 1], o[8 * i + 2], o[8 * i + 3], o[8 * i + 4],
+                       o[8 * i + 5], o[8 * i + 6], o[8 * i + 7]);
+            }
+          }
+        }
+      }
+      // release the accumulator stage
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still be reading / writing this CTA's exchange buffers
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace d3dp
