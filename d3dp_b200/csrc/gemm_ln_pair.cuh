@@ -6,8 +6,9 @@
 // would serialise MMA and epilogue.  Here a CTA pair shares each 128-row tile: CTA `rank` computes columns
 // [256*rank, 256*rank+256), so each SM holds two 256-column accumulator stages and the epilogue of tile i overlaps
 // the MMAs of tile i+1.  Row statistics are combined across the four 128-column quarters (2 epilogue groups x 2
-// CTAs) with Chan's parallel mean/M2 formula: every thread owns one row-quarter, publishes (mean, M2) to both CTAs'
-// shared memory (st.shared::cluster) and the exchange is closed by an mbarrier that counts warps of both CTAs.
+// CTAs) with Chan's parallel mean/M2 formula: every thread owns one row-quarter and publishes its (mean, M2) to both
+// CTAs with st.async (data + mbarrier complete_tx in one operation: no fences, no L1 flush); one mbarrier per TMEM
+// lane quadrant, so only the eight warps that share rows wait for each other.
 // The residual tile is streamed by TMA into a small swizzled ring (no uncoalesced row-per-thread global loads);
 // outputs leave with 256-bit stores, one full 32 B sector per lane.
 //
@@ -46,8 +47,8 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* rfull_bar = tempty_bar + 2;          // [g*RING + slot]
   uint64_t* rempty_bar = rfull_bar + 2 * RING;
-  uint64_t* xch_bar = rempty_bar + 2 * RING;     // [buf]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(xch_bar + 2);
+  uint64_t* xch_bar = rempty_bar + 2 * RING;     // [buf*4 + quad]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(xch_bar + 8);
   float2* xch = reinterpret_cast<float2*>(smem + L::XCH_OFFSET);
   float* sprm = reinterpret_cast<float*>(smem + L::PARAM_OFFSET);
 
@@ -72,8 +73,8 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], 8);
-      mbar_init(&xch_bar[a], 16);  // 8 epilogue warps of each CTA of the pair
     }
+    for (int i = 0; i < 8; ++i) mbar_init(&xch_bar[i], 1);  // armed per exchange; data arrives as tx bytes
     for (int i = 0; i < 2 * RING; ++i) {
       mbar_init(&rfull_bar[i], 1);
       mbar_init(&rempty_bar[i], 4);
@@ -141,9 +142,16 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 2) {
     // ------------------------------------------------------------------ residual TMA loader (x tile, 32-col chunks)
     if (lane == 0) {
+      // pull a tile's A operand (rank 0 only: the pair shares it) and this CTA's half of the x tile into L2
+      auto prefetch_tile = [&](int tile) {
+        if (rank == 0)
+          for (int kb = 0; kb < KB; ++kb) tma_prefetch_l2_2d(&tmA, kb * 64, tile * 128);
+        for (int c = 0; c < 8; ++c) tma_prefetch_l2_2d(&tmX, ncol0 + c * 32, tile * 128);
+      };
       int slot = 0;
       uint32_t ph = 0;
       for (int tile = cluster_id; tile < tiles_m; tile += num_clusters) {
+        if (tile + num_clusters < tiles_m) prefetch_tile(tile + num_clusters);
         for (int c = 0; c < 4; ++c) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
@@ -165,37 +173,33 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int r = quad * 32 + lane;   // tile row == TMEM lane
     const int lcol0 = g * 128;        // first local column
     const int qd = rank * 2 + g;      // quarter index of this thread's columns within the 512-wide row
-    const uint32_t peer = rank ^ 1u;
-    const uint32_t xch_local = smem_u32(xch);
-    const uint32_t xch_remote = mapa_u32(xch_local, peer);
-    const uint32_t xbar_remote0 = mapa_u32(smem_u32(&xch_bar[0]), peer);
     int as = 0, rslot = 0, xn = 0;
     uint32_t aph = 0, rph = 0;
 
-    // publish this row-quarter's (mean, M2), wait for all four quarters, return the row's mean and rstd
+    // publish this row-quarter's (mean, M2) to both CTAs, wait for the four quarters of the row, return mean / rstd
     auto exchange = [&](float m_loc, float m2_loc, float eps, float& mean, float& rstd) {
       const int buf = xn & 1;
+      uint64_t* bar = &xch_bar[buf * 4 + quad];
       const uint32_t off = static_cast<uint32_t>(((buf * 4 + qd) * 128 + r) * 8);
-      xch[(buf * 4 + qd) * 128 + r] = make_float2(m_loc, m2_loc);
-      st_cluster_f32x2(xch_remote + off, m_loc, m2_loc);
-      fence_acq_rel_cluster();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive_cluster(smem_u32(&xch_bar[buf]));            // own CTA
-        mbar_arrive_cluster(xbar_remote0 + buf * 8);             // peer CTA
-      }
-      mbar_wait_cluster(&xch_bar[buf], (xn >> 1) & 1);
-      float ms[4], m2s[4];
+      if (g == 0 && lane == 0) mbar_expect_tx(bar, 2 * 2 * 32 * 8);  // 8 B from each of the 4 warps x 32 lanes of this quadrant
+#pragma unroll
+      for (uint32_t dst = 0; dst < 2; ++dst)
+        st_async_f32x2(mapa_u32(smem_u32(xch), dst) + off, m_loc, m2_loc, mapa_u32(smem_u32(bar), dst));
+      mbar_wait(bar, (xn >> 1) & 1);
+      const float2* row = xch + buf * 4 * 128 + r;
+      float msum = 0.f, m2 = 0.f;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float2 t = xch[(buf * 4 + q) * 128 + r];
-        ms[q] = t.x;
-        m2s[q] = t.y;
+        const float2 t = row[q * 128];
+        msum += t.x;
+        m2 += t.y;
       }
-      mean = 0.25f * ((ms[0] + ms[1]) + (ms[2] + ms[3]));
-      float m2 = (m2s[0] + m2s[1]) + (m2s[2] + m2s[3]);
+      mean = 0.25f * msum;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) m2 = fmaf(128.0f * (ms[q] - mean), ms[q] - mean, m2);
+      for (int q = 0; q < 4; ++q) {
+        const float dm = row[q * 128].x - mean;
+        m2 = fmaf(128.0f * dm, dm, m2);
+      }
       rstd = rsqrtf(m2 * (1.0f / 512.0f) + eps);
       ++xn;
     };
@@ -210,8 +214,8 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256 + lcol0;
 
-      // ---- pass 1: v = acc + bias + residual -> TMEM ; row-quarter sum
-      float sum = 0.f;
+      // ---- pass 1: v = acc + bias + residual -> TMEM ; shifted one-pass sums (pivot = first value of the quarter)
+      float s1 = 0.f, s2 = 0.f, pv = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
@@ -234,7 +238,10 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float t = __uint_as_float(v[i]) + sprm[lcol0 + c * 32 + i] + res[i];
-          sum += t;
+          if (c == 0 && i == 0) pv = t;
+          const float d = t - pv;
+          s1 += d;
+          s2 = fmaf(d, d, s2);
           v[i] = __float_as_uint(t);
         }
         tmem_st32(taddr + c * 32, v);
@@ -248,24 +255,12 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       tmem_st_wait();
-      const float m_loc = sum * (1.0f / 128.0f);
-      // ---- pass 2: M2 about the local mean
-      float m2_loc = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float d = __uint_as_float(v[i]) - m_loc;
-          m2_loc = fmaf(d, d, m2_loc);
-        }
-      }
+      const float m_loc = pv + s1 * (1.0f / 128.0f);
+      const float m2_loc = fmaxf(s2 - s1 * s1 * (1.0f / 128.0f), 0.f);
       float mean, rstd;
       exchange(m_loc, m2_loc, p.ln_a_eps, mean, rstd);
-      // ---- pass 3: y = LN_a(v)
-      float sum2 = 0.f;
+      // ---- pass 2: y = LN_a(v) ; LN2: shifted sums of y for the second LayerNorm
+      float t1 = 0.f, t2 = 0.f, py = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
@@ -277,7 +272,10 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float y = (__uint_as_float(v[i]) - mean) * rstd * sprm[256 + n + i] + sprm[512 + n + i];
           if constexpr (EPI == EPI_RES_LN2) {
             if (p.tpos) y += __ldg(p.tpos + static_cast<size_t>(f) * 512 + ncol0 + n + i);
-            sum2 += y;
+            if (c == 0 && i == 0) py = y;
+            const float d = y - py;
+            t1 += d;
+            t2 = fmaf(d, d, t2);
           }
           v[i] = __float_as_uint(y);
         }
@@ -308,19 +306,8 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if constexpr (EPI == EPI_RES_LN2) {
         if (has_b) {  // uniform over the grid
           tmem_st_wait();
-          const float m_loc2 = sum2 * (1.0f / 128.0f);
-          float m2_loc2 = 0.f;
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            tmem_ld32(taddr + c * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float d = __uint_as_float(v[i]) - m_loc2;
-              m2_loc2 = fmaf(d, d, m2_loc2);
-            }
-          }
+          const float m_loc2 = py + t1 * (1.0f / 128.0f);
+          const float m2_loc2 = fmaxf(t2 - t1 * t1 * (1.0f / 128.0f), 0.f);
           float mean2, rstd2;
           exchange(m_loc2, m2_loc2, p.ln_b_eps, mean2, rstd2);
 #pragma unroll 1
