@@ -209,6 +209,11 @@ int launch_gemm(d3dp_handle* h, int mode, const CUtensorMap& tmA, const CUtensor
     int rc = make_tmap(h, &tmC, p.x, p.M, 512, 128, /*f32=*/true);
     if (rc) return rc;
   }
+  CUtensorMap tmA64 = tmA;  // LN modes: 64-row boxes (each CTA of the pair fetches half of the A tile and multicasts)
+  if (mode == EPI_RES_LN || mode == EPI_RES_LN2) {
+    int rc = make_tmap(h, &tmA64, p.a_ptr, p.M, p.K, 64);
+    if (rc) return rc;
+  }
   const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int bn = (mode == EPI_BIAS_F16 || mode == EPI_BIAS_GELU_F16) ? 256 : 512;
   if (p.N % bn != 0 || p.K % GEMM_BK != 0 || p.M <= 0) return fail(h, D3DP_E_INVALID, "gemm: unsupported shape");
@@ -220,8 +225,8 @@ int launch_gemm(d3dp_handle* h, int mode, const CUtensorMap& tmA, const CUtensor
     case EPI_RES_LN:
     case EPI_RES_LN2: {
       const int pairs = tiles_m < h->num_sms / 2 ? tiles_m : h->num_sms / 2;  // one CTA pair (cluster) per M tile
-      if (mode == EPI_RES_LN) k_gemm_proj<<<2 * pairs, 352, kSmemN512, st>>>(tmA, tmB, tmC, p);
-      else k_gemm_fc2<<<2 * pairs, 352, kSmemN512, st>>>(tmA, tmB, tmC, p);
+      if (mode == EPI_RES_LN) k_gemm_proj<<<2 * pairs, 352, kSmemN512, st>>>(tmA64, tmB, tmC, p);
+      else k_gemm_fc2<<<2 * pairs, 352, kSmemN512, st>>>(tmA64, tmB, tmC, p);
       break;
     }
     default: return fail(h, D3DP_E_INVALID, "gemm: bad mode");
@@ -365,7 +370,7 @@ int run_denoiser(d3dp_handle* h, const Workspace& w, const float* x2d, const flo
       p = GemmParams{};
       p.F = F; p.M = T; p.N = 512; p.K = 512;
       p.bias = static_cast<const float*>(bw.projb->dev);
-      p.out16 = w.a16; p.ldo = 512; p.x = w.x;
+      p.out16 = w.a16; p.ldo = 512; p.x = w.x; p.a_ptr = w.o16;
       p.ln_a_g = static_cast<const float*>(bw.n2w->dev);
       p.ln_a_b = static_cast<const float*>(bw.n2b->dev);
       p.ln_a_eps = 1e-6f;
@@ -380,7 +385,7 @@ int run_denoiser(d3dp_handle* h, const Workspace& w, const float* x2d, const flo
       p = GemmParams{};
       p.F = F; p.M = T; p.N = 512; p.K = 1024;
       p.bias = static_cast<const float*>(bw.fc2b->dev);
-      p.out16 = w.a16; p.ldo = 512; p.x = w.x;
+      p.out16 = w.a16; p.ldo = 512; p.x = w.x; p.a_ptr = w.qkv16;
       p.ln_a_g = which == 0 ? ln_s_g : ln_t_g;
       p.ln_a_b = which == 0 ? ln_s_b : ln_t_b;
       p.ln_a_eps = 1e-6f;
@@ -693,7 +698,7 @@ int d3dp_test_gemm(d3dp_handle* h, int32_t mode, const void* a16, const void* w1
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.bias = bias;
   p.out16 = static_cast<__half*>(out16);
-  p.ldo = N; p.x = x;
+  p.ldo = N; p.x = x; p.a_ptr = a16;
   p.ln_a_g = g_a; p.ln_a_b = b_a; p.ln_a_eps = eps_a;
   p.ln_b_g = g_b; p.ln_b_b = b_b; p.ln_b_eps = eps_b;
   p.tpos = tpos; p.F = F > 0 ? F : 1;

@@ -68,7 +68,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmX);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], 2);  // the A half this CTA multicasts lands in both CTAs: both MMAs must be done
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -107,7 +107,8 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[s], kb * 64, tile * 128);
+          // the pair shares the A tile: each CTA fetches 64 of its 128 rows and multicasts them to both
+          tma_load_2d_mc(sa + rank * (L::A_BYTES / 2), &tmA, &full_bar[s], kb * 64, tile * 128 + rank * 64, 0x3);
           tma_load_2d(sa + L::A_BYTES, &tmB, &full_bar[s], kb * 64, ncol0);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -132,7 +133,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int k = 0; k < 4; ++k)
             mma_f16_ss(d_tmem, make_sdesc_sw128(a_base + k * 32, 16, 1024), make_sdesc_sw128(b_base + k * 32, 16, 1024),
                        idesc, (kb | k) != 0 ? 1u : 0u);
-          tc_commit(&empty_bar[s]);
+          tc_commit_mc(&empty_bar[s], 0x3);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         tc_commit(&tfull_bar[as]);
@@ -142,10 +143,8 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 2) {
     // ------------------------------------------------------------------ residual TMA loader (x tile, 32-col chunks)
     if (lane == 0) {
-      // pull a tile's A operand (rank 0 only: the pair shares it) and this CTA's half of the x tile into L2
+      // pull this CTA's half of the next x tile into L2
       auto prefetch_tile = [&](int tile) {
-        if (rank == 0)
-          for (int kb = 0; kb < KB; ++kb) tma_prefetch_l2_2d(&tmA, kb * 64, tile * 128);
         for (int c = 0; c < 8; ++c) tma_prefetch_l2_2d(&tmX, ncol0 + c * 32, tile * 128);
       };
       int slot = 0;

@@ -25,6 +25,7 @@ struct GemmParams {
   __half* out16;      // F16 modes: [M, ldo];  LN modes: LN output [M, 512] (may be null -> not written)
   int ldo;
   float* x;  // LN modes: residual stream [M,512] fp32, updated in place
+  const void* a_ptr;  // LN modes: the A operand [M,K] fp16 (host side builds a 64-row-box tensor map from it)
   const float* ln_a_g;
   const float* ln_a_b;
   float ln_a_eps;
