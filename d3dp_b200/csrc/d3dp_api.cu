@@ -32,7 +32,8 @@ struct Slot {
   bool f16 = false;
   bool set = false;
   int rows = 0, cols = 0;  // GEMM weights: [rows=N, cols=K]
-  CUtensorMap tmap;        // GEMM weights only
+  CUtensorMap tmap;        // GEMM weights only: box {64, 256 rows} (LN pair kernel: one N half per CTA)
+  CUtensorMap tmap128;     // box {64, 128 rows} (qkv / fc1 kernel: half a weight slab, multicast to the CTA pair)
 };
 
 struct BlockW {
@@ -178,12 +179,12 @@ int set_smem_attr(d3dp_handle* h, KernelT k, int bytes) {
 
 // kernel instantiations used by the pipeline
 constexpr int kStagesN256 = 3;
-auto* const k_gemm_qkv = gemm_tcgen05_kernel<256, EPI_BIAS_F16, kStagesN256, 8>;
-auto* const k_gemm_fc1 = gemm_tcgen05_kernel<256, EPI_BIAS_GELU_F16, kStagesN256, 8>;
+auto* const k_gemm_qkv = gemm_tcgen05_kernel<EPI_BIAS_F16, kStagesN256>;
+auto* const k_gemm_fc1 = gemm_tcgen05_kernel<EPI_BIAS_GELU_F16, kStagesN256>;
 constexpr int kLnStages = 3, kLnRing = 2;
 auto* const k_gemm_proj = gemm_ln_pair_kernel<EPI_RES_LN, kLnStages, kLnRing>;
 auto* const k_gemm_fc2 = gemm_ln_pair_kernel<EPI_RES_LN2, kLnStages, kLnRing>;
-constexpr int kSmemN256 = GemmSmem<256, kStagesN256>::TOTAL;
+constexpr int kSmemN256 = GemmSmem<kStagesN256>::TOTAL;
 constexpr int kSmemN512 = LnPairSmem<kLnStages, kLnRing>::TOTAL;
 
 int ensure_attrs(d3dp_handle* h) {
@@ -217,11 +218,15 @@ int launch_gemm(d3dp_handle* h, int mode, const CUtensorMap& tmA, const CUtensor
   const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int bn = (mode == EPI_BIAS_F16 || mode == EPI_BIAS_GELU_F16) ? 256 : 512;
   if (p.N % bn != 0 || p.K % GEMM_BK != 0 || p.M <= 0) return fail(h, D3DP_E_INVALID, "gemm: unsupported shape");
-  const int tiles = tiles_m * (p.N / bn);
-  const int grid = tiles < h->num_sms ? tiles : h->num_sms;
   switch (mode) {
-    case EPI_BIAS_F16: k_gemm_qkv<<<grid, 64 + 8 * 32, kSmemN256, st>>>(tmA, tmB, tmC, p); break;
-    case EPI_BIAS_GELU_F16: k_gemm_fc1<<<grid, 64 + 8 * 32, kSmemN256, st>>>(tmA, tmB, tmC, p); break;
+    case EPI_BIAS_F16:
+    case EPI_BIAS_GELU_F16: {
+      const int ctiles = ((tiles_m + 1) / 2) * (p.N / bn);  // (M-tile pair, N tile) per 2-CTA cluster
+      const int clusters = ctiles < h->num_sms / 2 ? ctiles : h->num_sms / 2;
+      if (mode == EPI_BIAS_F16) k_gemm_qkv<<<2 * clusters, GEMM_THREADS, kSmemN256, st>>>(tmA, tmB, tmC, p);
+      else k_gemm_fc1<<<2 * clusters, GEMM_THREADS, kSmemN256, st>>>(tmA, tmB, tmC, p);
+      break;
+    }
     case EPI_RES_LN:
     case EPI_RES_LN2: {
       const int pairs = tiles_m < h->num_sms / 2 ? tiles_m : h->num_sms / 2;  // one CTA pair (cluster) per M tile
@@ -361,7 +366,7 @@ int run_denoiser(d3dp_handle* h, const Workspace& w, const float* x2d, const flo
       p.M = T; p.N = 1536; p.K = 512;
       p.bias = static_cast<const float*>(bw.qkvb->dev);
       p.out16 = w.qkv16; p.ldo = 1536;
-      if ((rc = launch_gemm(h, EPI_BIAS_F16, tm_a, bw.qkvw->tmap, p, st))) return rc;
+      if ((rc = launch_gemm(h, EPI_BIAS_F16, tm_a, bw.qkvw->tmap128, p, st))) return rc;
       // attention
       if (which == 0) rc = launch_attn_spatial(h, w.qkv16, w.o16, n_streams, st);
       else rc = launch_attn_temporal(h, w.qkv16, w.o16, n_streams, st);
@@ -380,7 +385,7 @@ int run_denoiser(d3dp_handle* h, const Workspace& w, const float* x2d, const flo
       p.F = F; p.M = T; p.N = 1024; p.K = 512;
       p.bias = static_cast<const float*>(bw.fc1b->dev);
       p.out16 = w.qkv16; p.ldo = 1024;
-      if ((rc = launch_gemm(h, EPI_BIAS_GELU_F16, tm_a, bw.fc1w->tmap, p, st))) return rc;
+      if ((rc = launch_gemm(h, EPI_BIAS_GELU_F16, tm_a, bw.fc1w->tmap128, p, st))) return rc;
       // x = shared_norm(x + fc2(hidden)) (+Tpos after S0) ; a16 = next block's norm1(x)
       p = GemmParams{};
       p.F = F; p.M = T; p.N = 512; p.K = 1024;
@@ -518,6 +523,7 @@ int d3dp_set_weight(d3dp_handle* h, const char* name, const float* data, int64_t
     CK(cudaGetLastError());
     int rc = make_tmap(h, &s.tmap, s.dev, s.rows, s.cols, 256);
     if (rc) return rc;
+    if ((rc = make_tmap(h, &s.tmap128, s.dev, s.rows, s.cols, 128))) return rc;
   } else {
     CK(cudaMemcpyAsync(s.dev, data, static_cast<size_t>(numel) * 4, cudaMemcpyDeviceToDevice, st));
   }
@@ -694,7 +700,7 @@ int d3dp_test_gemm(d3dp_handle* h, int32_t mode, const void* a16, const void* w1
   if ((rc = ensure_attrs(h))) return rc;
   CUtensorMap tmA, tmB;
   if ((rc = make_tmap(h, &tmA, a16, M, K, 128))) return rc;
-  if ((rc = make_tmap(h, &tmB, w16, N, K, 256))) return rc;
+  if ((rc = make_tmap(h, &tmB, w16, N, K, mode < 2 ? 128 : 256))) return rc;
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.bias = bias;
   p.out16 = static_cast<__half*>(out16);
