@@ -134,33 +134,78 @@ attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParam
         const int qrow = mt * 128 + r;
         mbar_wait(&sfull_bar[mt], iph);
         tc_fence_after();
-        // pass 1: row max over the valid keys
+        // Software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is processed; only the
+        // chunk that straddles F carries a key mask.
+        const int full_chunks = p.F >> 5;   // chunks whose 32 keys are all valid
+        const int tail = p.F & 31;          // valid keys in chunk `full_chunks` (0: none)
+        // ---- pass 1: row max over the valid keys
         float mx = -INFINITY;
-        for (int c = 0; c < nchunks; ++c) {
-          uint32_t v[32];
-          tmem_ld32(t_s + c * 32, v);
-          tmem_ld_wait();
+        {
+          uint32_t va[32], vb[32];
+          tmem_ld32(t_s, va);
+          for (int c = 0; c < nchunks; c += 2) {
+            tmem_ld_wait();
+            if (c + 1 < nchunks) tmem_ld32(t_s + (c + 1) * 32, vb);
+            if (c < full_chunks) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < p.F) mx = fmaxf(mx, __uint_as_float(v[i]));
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(va[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < tail) mx = fmaxf(mx, __uint_as_float(va[i]));
+            }
+            if (c + 1 < nchunks) {
+              tmem_ld_wait();
+              if (c + 2 < nchunks) tmem_ld32(t_s + (c + 2) * 32, va);
+              if (c + 1 < full_chunks) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(vb[i]));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < tail) mx = fmaxf(mx, __uint_as_float(vb[i]));
+              }
+            }
+          }
         }
         const float moff = mx * p.scale_log2e;
-        // pass 2: p = exp2(s*c - max*c), row sum, fp16 P written over the consumed part of S
+        // ---- pass 2: p = exp2(s*c - max*c), row sum, fp16 P written over the consumed part of S
         float sum = 0.f;
-        for (int c = 0; c < nchunks; ++c) {
-          uint32_t v[32];
-          tmem_ld32(t_s + c * 32, v);
-          tmem_ld_wait();
+        auto expo_chunk = [&](const uint32_t (&v)[32], int c) {
           uint32_t o[16];
+          if (c < full_chunks) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int k0 = c * 32 + 2 * i;
-            float a = k0 < p.F ? exp2f(__uint_as_float(v[2 * i]) * p.scale_log2e - moff) : 0.f;
-            float b = k0 + 1 < p.F ? exp2f(__uint_as_float(v[2 * i + 1]) * p.scale_log2e - moff) : 0.f;
-            sum += a + b;
-            o[i] = pack_half2(a, b);
+            for (int i = 0; i < 16; ++i) {
+              const float a = ex2_approx(fmaf(__uint_as_float(v[2 * i]), p.scale_log2e, -moff));
+              const float b = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2e, -moff));
+              sum += a + b;
+              o[i] = pack_half2(a, b);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float a = 2 * i < tail ? ex2_approx(fmaf(__uint_as_float(v[2 * i]), p.scale_log2e, -moff)) : 0.f;
+              const float b =
+                  2 * i + 1 < tail ? ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2e, -moff)) : 0.f;
+              sum += a + b;
+              o[i] = pack_half2(a, b);
+            }
           }
           tmem_st16(t_s + c * 16, o);
+        };
+        {
+          uint32_t va[32], vb[32];
+          tmem_ld32(t_s, va);
+          for (int c = 0; c < nchunks; c += 2) {
+            tmem_ld_wait();
+            if (c + 1 < nchunks) tmem_ld32(t_s + (c + 1) * 32, vb);
+            expo_chunk(va, c);
+            if (c + 1 < nchunks) {
+              tmem_ld_wait();
+              if (c + 2 < nchunks) tmem_ld32(t_s + (c + 2) * 32, va);
+              expo_chunk(vb, c + 1);
+            }
+          }
         }
         tmem_st_wait();
         tc_fence_before();
@@ -177,13 +222,19 @@ attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParam
           tmem_ld32(t_s + 128 + c * 32, v);
           tmem_ld_wait();
           if (qrow < p.F) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              dst[i] = make_uint4(pack_half2(__uint_as_float(v[8 * i]) * inv, __uint_as_float(v[8 * i + 1]) * inv),
-                                  pack_half2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv),
-                                  pack_half2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv),
-                                  pack_half2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv));
+            for (int i = 0; i < 2; ++i) {
+              const uint32_t* u = v + 16 * i;
+              stg256(orow + c * 32 + 16 * i,
+                     pack_half2(__uint_as_float(u[0]) * inv, __uint_as_float(u[1]) * inv),
+                     pack_half2(__uint_as_float(u[2]) * inv, __uint_as_float(u[3]) * inv),
+                     pack_half2(__uint_as_float(u[4]) * inv, __uint_as_float(u[5]) * inv),
+                     pack_half2(__uint_as_float(u[6]) * inv, __uint_as_float(u[7]) * inv),
+                     pack_half2(__uint_as_float(u[8]) * inv, __uint_as_float(u[9]) * inv),
+                     pack_half2(__uint_as_float(u[10]) * inv, __uint_as_float(u[11]) * inv),
+                     pack_half2(__uint_as_float(u[12]) * inv, __uint_as_float(u[13]) * inv),
+                     pack_half2(__uint_as_float(u[14]) * inv, __uint_as_float(u[15]) * inv));
+            }
           }
         }
         tc_fence_before();

@@ -162,6 +162,11 @@ __device__ __forceinline__ void stg256(void* p, uint32_t a, uint32_t b, uint32_t
                "r"(f), "r"(g), "r"(h)
                : "memory");
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 // approximate reciprocal (MUFU.RCP), ~1 ulp
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
