@@ -25,9 +25,10 @@ def gather_hypotheses(preds, world, group=None):
     if world == 1:
         return preds
     preds = preds.contiguous()
-    out = torch.empty((world,) + tuple(preds.shape), dtype=preds.dtype, device=preds.device)
-    dist.all_gather_into_tensor(out, preds, group=group)
     B, K, h = preds.shape[:3]
+    out = torch.empty((world * B,) + tuple(preds.shape[1:]), dtype=preds.dtype, device=preds.device)
+    dist.all_gather_into_tensor(out, preds, group=group)  # rank-major concatenation along dim 0
+    out = out.reshape((world,) + tuple(preds.shape))
     return out.permute(1, 2, 0, 3, 4, 5, 6).reshape(B, K, world * h, *preds.shape[3:])
 
 

@@ -1,0 +1,112 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports what the header declares, the drop-in classes expose the
+reference's surface, and the host-side helpers behave."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_symbol_in_header():
+    from d3dp_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "d3dp_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(d3dp_[a-z0-9_]+)\s*\(", header)))
+    assert declared, "no declarations parsed"
+    assert sorted(_lib.SYMBOLS) == declared, "bindings out of sync with the header"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.d3dp_version()
+
+
+def test_engine_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from d3dp_b200._lib import D3dpError
+    from d3dp_b200.engine import Engine
+    with pytest.raises(D3dpError):
+        Engine(frames=27)
+
+
+def test_d3dp_module_surface_and_state_dict():
+    from d3dp_b200 import D3DP
+    from tests.util import JL, JR, make_args
+    m = D3DP(make_args(27), JL, JR, is_train=False, num_proposals=3, sampling_timesteps=5)
+    sd = m.state_dict()
+    assert len(sd) == 220  # 12 float64 schedule buffers + 208 pose_estimator tensors
+    bufs = ["betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+            "log_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+            "posterior_variance", "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2"]
+    assert list(sd.keys())[:12] == bufs
+    assert all(sd[b].dtype == torch.float64 and sd[b].shape == (1000,) for b in bufs)
+    for k in ["pose_estimator.Spatial_pos_embed", "pose_estimator.Temporal_pos_embed",
+              "pose_estimator.Spatial_patch_to_embedding.weight", "pose_estimator.time_mlp.1.weight",
+              "pose_estimator.time_mlp.3.bias", "pose_estimator.STEblocks.7.attn.qkv.weight",
+              "pose_estimator.TTEblocks.0.mlp.fc2.bias", "pose_estimator.Spatial_norm.weight",
+              "pose_estimator.Temporal_norm.bias", "pose_estimator.head.0.weight", "pose_estimator.head.1.bias"]:
+        assert k in sd, k
+    assert sd["pose_estimator.Temporal_pos_embed"].shape == (1, 27, 512)
+    assert sum(v.numel() for k, v in sd.items() if k.startswith("pose_estimator.")) == 34724867
+    assert m._time_list() == [999, 799, 599, 399, 199, -1]
+    for attr in ("forward", "ddim_sample", "ddim_sample_flip", "q_sample", "predict_noise_from_start",
+                 "prepare_targets", "pose_estimator"):
+        assert hasattr(m, attr)
+    # strict load of a DataParallel-style checkpoint (keys prefixed `module.`, main.py:630) works like the reference
+    dp_state = {"module." + k: v for k, v in sd.items()}
+    torch.nn.DataParallel(m).load_state_dict(dp_state, strict=True) if torch.cuda.is_available() else \
+        m.load_state_dict({k[len("module."):]: v for k, v in dp_state.items()}, strict=True)
+    with pytest.raises(RuntimeError):  # parameters on the CPU: there is no CPU path
+        m.pose_estimator.engine()
+
+
+def test_default_init_matches_reference_when_available():
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip("reference tree not present on this machine")
+    from d3dp_b200 import D3DP
+    from tests.util import JL, JR, make_args
+    torch.manual_seed(0)
+    mine = D3DP(make_args(9), JL, JR, is_train=False, num_proposals=1, sampling_timesteps=1).state_dict()
+    dp = rh.import_reference()
+    torch.manual_seed(0)
+    ref = dp.D3DP(rh.make_args(9), JL, JR, is_train=False, num_proposals=1, sampling_timesteps=1).state_dict()
+    assert list(mine.keys()) == list(ref.keys())
+    for k in ref:
+        assert mine[k].dtype == ref[k].dtype and torch.equal(mine[k], ref[k]), k
+
+
+def test_unsupported_configurations_raise():
+    from d3dp_b200 import MixSTE2
+    with pytest.raises(ValueError):
+        MixSTE2(num_frame=27, embed_dim_ratio=256, depth=8)
+    with pytest.raises(ValueError):
+        MixSTE2(num_frame=351, embed_dim_ratio=512, depth=8)
+
+
+def test_flip_permutation_and_synthetic_determinism():
+    from d3dp_b200.engine import flip_permutation
+    from d3dp_b200.synthetic import (H36M_JOINTS_LEFT as JL, H36M_JOINTS_RIGHT as JR, flip_2d,
+                                     synthetic_pose_estimator_state)
+    perm = flip_permutation(JL, JR)
+    assert sorted(perm) == list(range(17)) and [perm[perm[j]] for j in range(17)] == list(range(17))
+    x = torch.randn(2, 5, 17, 2)
+    ref = x.clone()
+    ref[..., 0] *= -1
+    assert torch.equal(flip_2d(x), ref[:, :, perm])
+    a, b = synthetic_pose_estimator_state(9, depth=1, seed=3), synthetic_pose_estimator_state(9, depth=1, seed=3)
+    assert all(torch.equal(a[k], b[k]) for k in a) and len(a) == 8 + 24 + 8
+    assert abs(a["STEblocks.0.attn.qkv.weight"].double().sum().item() - (-1.1920928955078125e-07)) < 50  # stable draw
+    c = synthetic_pose_estimator_state(9, depth=1, seed=4)
+    assert not torch.equal(a["head.1.weight"], c["head.1.weight"])
+
+
+def test_shard_range_partitions_hypotheses():
+    from d3dp_b200.distributed import shard_range
+    for H in (1, 5, 20, 21, 160):
+        for W in (1, 2, 3, 4, 8):
+            parts = [shard_range(H, W, r) for r in range(W)]
+            assert parts[0][0] == 0 and sum(n for _, n in parts) == H
+            assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(W - 1))
+            assert max(n for _, n in parts) - min(n for _, n in parts) <= 1
