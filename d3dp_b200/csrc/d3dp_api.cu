@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -185,6 +186,18 @@ constexpr int kLnStages = 3, kLnRing = 2;
 auto* const k_gemm_proj = gemm_ln_pair_kernel<EPI_RES_LN, kLnStages, kLnRing>;
 auto* const k_gemm_fc2 = gemm_ln_pair_kernel<EPI_RES_LN2, kLnStages, kLnRing>;
 constexpr int kSmemN256 = GemmSmem<kStagesN256>::TOTAL;
+constexpr int kStages2Sm = 4;
+auto* const k_gemm2_qkv = gemm_2sm_kernel<EPI_BIAS_F16, kStages2Sm>;
+auto* const k_gemm2_fc1 = gemm_2sm_kernel<EPI_BIAS_GELU_F16, kStages2Sm>;
+constexpr int kSmem2Sm = Gemm2SmSmem<kStages2Sm>::TOTAL;
+// D3DP_GEMM_1SM=1 selects the single-CTA-MMA kernel (A/B comparisons); default is the cta_group::2 kernel
+bool use_2sm() {
+  static const bool v = [] {
+    const char* e = getenv("D3DP_GEMM_1SM");
+    return !(e && e[0] == '1');
+  }();
+  return v;
+}
 constexpr int kSmemN512 = LnPairSmem<kLnStages, kLnRing>::TOTAL;
 
 int ensure_attrs(d3dp_handle* h) {
@@ -192,6 +205,8 @@ int ensure_attrs(d3dp_handle* h) {
   int rc;
   if ((rc = set_smem_attr(h, k_gemm_qkv, kSmemN256))) return rc;
   if ((rc = set_smem_attr(h, k_gemm_fc1, kSmemN256))) return rc;
+  if ((rc = set_smem_attr(h, k_gemm2_qkv, kSmem2Sm))) return rc;
+  if ((rc = set_smem_attr(h, k_gemm2_fc1, kSmem2Sm))) return rc;
   if ((rc = set_smem_attr(h, k_gemm_proj, kSmemN512))) return rc;
   if ((rc = set_smem_attr(h, k_gemm_fc2, kSmemN512))) return rc;
   if ((rc = set_smem_attr(h, attn_temporal_kernel, ATT_SMEM_BYTES))) return rc;
@@ -223,8 +238,14 @@ int launch_gemm(d3dp_handle* h, int mode, const CUtensorMap& tmA, const CUtensor
     case EPI_BIAS_GELU_F16: {
       const int ctiles = ((tiles_m + 1) / 2) * (p.N / bn);  // (M-tile pair, N tile) per 2-CTA cluster
       const int clusters = ctiles < h->num_sms / 2 ? ctiles : h->num_sms / 2;
-      if (mode == EPI_BIAS_F16) k_gemm_qkv<<<2 * clusters, GEMM_THREADS, kSmemN256, st>>>(tmA, tmB, tmC, p);
-      else k_gemm_fc1<<<2 * clusters, GEMM_THREADS, kSmemN256, st>>>(tmA, tmB, tmC, p);
+      if (use_2sm()) {
+        if (mode == EPI_BIAS_F16) k_gemm2_qkv<<<2 * clusters, GEMM_THREADS, kSmem2Sm, st>>>(tmA, tmB, tmC, p);
+        else k_gemm2_fc1<<<2 * clusters, GEMM_THREADS, kSmem2Sm, st>>>(tmA, tmB, tmC, p);
+      } else if (mode == EPI_BIAS_F16) {
+        k_gemm_qkv<<<2 * clusters, GEMM_THREADS, kSmemN256, st>>>(tmA, tmB, tmC, p);
+      } else {
+        k_gemm_fc1<<<2 * clusters, GEMM_THREADS, kSmemN256, st>>>(tmA, tmB, tmC, p);
+      }
       break;
     }
     case EPI_RES_LN:

@@ -246,3 +246,194 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 }  // namespace d3dp
+
+// =====================================================================================================================
+// cta_group::2 variant: the CTA pair computes one 256x256 tile with a single MMA stream (UMMA M=256).  Each CTA stages
+// its own 128 A rows and HALF of the weight slab (128 of the 256 N rows), so per k-block an SM reads 8 KB instead of
+// 12 KB of operands from shared memory and fills 32 KB instead of 48 KB by TMA — the single-CTA kernel above is bound
+// by shared-memory bandwidth (MMA operand reads + TMA fills ~ 190 B/clk of 128).  The leader CTA (rank 0) issues all
+// MMAs; both CTAs' TMA loads complete on the leader's `full` barriers; MMA commits are multicast to both CTAs.
+namespace d3dp {
+
+template <int STAGES>
+struct Gemm2SmSmem {
+  static constexpr int A_BYTES = 128 * GEMM_BK * 2;       // this CTA's 128 rows of A
+  static constexpr int B_BYTES = 128 * GEMM_BK * 2;       // this CTA's half (128 rows) of the 256-row weight slab
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;  // full[STAGES] empty[STAGES] tfull[2] tempty[2], tmem ptr
+  static constexpr int PARAM_OFFSET = BAR_OFFSET + 256;
+  static constexpr int PARAM_FLOATS = 2560;
+  static constexpr int OUT_OFFSET = (PARAM_OFFSET + PARAM_FLOATS * 4 + 1023) / 1024 * 1024;
+  static constexpr int TOTAL = OUT_OFFSET + 2 * 2 * 16384 + 1024;
+};
+
+template <int EPI, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+  using L = Gemm2SmSmem<STAGES>;
+  static_assert(EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16, "fp16-output epilogues only");
+  constexpr int COLS_PER_THREAD = GEMM_BN / 2;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);  // used in the leader only
+  uint64_t* empty_bar = full_bar + STAGES;                                  // per CTA
+  uint64_t* tfull_bar = empty_bar + STAGES;                                 // per CTA
+  uint64_t* tempty_bar = tfull_bar + 2;                                     // used in the leader only
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* sprm = reinterpret_cast<float*>(smem + L::PARAM_OFFSET);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int pairs_m = (tiles_m + 1) / 2;
+  const int tiles_n = p.N / GEMM_BN;
+  const int num_ctiles = pairs_m * tiles_n;
+  const int KB = p.K / GEMM_BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);   // armed by the leader's producer; bytes arrive from both CTAs
+      mbar_init(&empty_bar[s], 1);  // one multicast MMA commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 2 * GEMM_EPI_WARPS);  // epilogue warps of both CTAs release the pair's accumulator
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<512>(tmem_ptr);
+  for (int i = threadIdx.x; i < p.N; i += blockDim.x) sprm[i] = p.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+        const int m_blk = (ct / tiles_n) * 2 + rank, n_blk = ct % tiles_n;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[s]), 0);
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * L::STAGE_BYTES);
+          tma_load_2d_2sm(sa, &tmA, leader_full, kb * GEMM_BK, m_blk * GEMM_BM);
+          tma_load_2d_2sm(sa + L::A_BYTES, &tmB, leader_full, kb * GEMM_BK, n_blk * GEMM_BN + rank * 128);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(256, 256, 0, 0);
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+        mbar_wait_cluster(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * GEMM_BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t b_base = a_base + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k)
+            mma_f16_ss_2sm(d_tmem, make_sdesc_sw128(a_base + k * 32, 16, 1024),
+                           make_sdesc_sw128(b_base + k * 32, 16, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit_2sm_mc(&empty_bar[s], 0x3);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        tc_commit_2sm_mc(&tfull_bar[as], 0x3);
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int split = ew >> 2;
+    const int r = quad * 32 + lane;
+    const int col0 = split * COLS_PER_THREAD;
+    uint8_t* gbuf = smem + L::OUT_OFFSET + split * 2 * 16384;
+    const bool leader = (ew & 3) == 0 && lane == 0;
+    const uint32_t tempty_leader0 = mapa_u32(smem_u32(&tempty_bar[0]), 0);
+    int as = 0;
+    uint32_t aph = 0;
+    for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+      const int m_blk = (ct / tiles_n) * 2 + rank, n_blk = ct % tiles_n;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * GEMM_BN + col0;
+      const int n0 = n_blk * GEMM_BN + col0;
+#pragma unroll 1
+      for (int sl = 0; sl < COLS_PER_THREAD / 64; ++sl) {
+        uint8_t* buf = gbuf + (sl & 1) * 16384;
+        if (leader) tma_store_wait_read<1>();
+        named_bar_sync(2 + split, 128);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = sl * 2 + cc;
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          uint32_t o[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 bb = *reinterpret_cast<const float2*>(sprm + n0 + c * 32 + 2 * i);
+            float a = __uint_as_float(v[2 * i]) + bb.x;
+            float b = __uint_as_float(v[2 * i + 1]) + bb.y;
+            if constexpr (EPI == EPI_BIAS_GELU_F16) {
+              a = gelu_erf(a);
+              b = gelu_erf(b);
+            }
+            o[i] = pack_half2(a, b);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int piece = cc * 4 + i;
+            *reinterpret_cast<uint4*>(buf + r * 128 + ((piece ^ (r & 7)) << 4)) =
+                make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          }
+        }
+        if (sl == COLS_PER_THREAD / 64 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_leader0 + as * 8);  // the leader's MMA thread owns the pair's TMEM
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2 + split, 128);
+        if (leader) {
+          tma_store_2d(&tmC, buf, n0 + sl * 64, m_blk * GEMM_BM);
+          tma_store_commit();
+        }
+      }
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+
+  tma_store_wait_all<0>();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
+}
+
+}  // namespace d3dp
