@@ -56,21 +56,22 @@ struct GemmSmem {
   static constexpr int TOTAL = OUT_OFFSET + 2 * 2 * 16384 + 1024 /*alignment slack*/;
 };
 
-// erf by Abramowitz & Stegun 7.1.26 (|abs error| <= 1.5e-7): branch-free, 2 MUFU + 7 FMA, so the fc1 epilogue
-// keeps up with the MMA pipe.  The result feeds an fp16 store (rel. 4.9e-4), so this is exact-erf GELU for all
-// practical purposes (reference: nn.GELU() default = erf form, common/mixste.py:24,39).
-__device__ __forceinline__ float erf_as(float x) {
-  const float ax = fabsf(x);
-  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
+// Exact-erf GELU (reference: nn.GELU() default, common/mixste.py:24,39) with erf by Abramowitz & Stegun 7.1.26
+// (|abs error| <= 1.5e-7, far below the fp16 rounding of the result), arranged for the epilogue's issue budget:
+// branch-free, 2 MUFU (rcp, ex2) + 12 FMA-pipe ops.  With zc = v * sqrt(log2 e / 2):  erf(|v|/sqrt 2) =
+// 1 - poly(t) * 2^(-zc^2),  t = 1 / (1 + (p / sqrt(log2 e)) |zc|);  gelu = v/2 + v/2 * sign(v) * erf(|v|/sqrt 2).
+__device__ __forceinline__ float gelu_erf(float v) {
+  const float zc = v * 0.84932180028801907f;                // v / sqrt(2) * sqrt(log2(e))
+  const float t = rcp_approx(fmaf(0.27273678890578706f, fabsf(zc), 1.0f));  // 0.3275911 / sqrt(log2(e))
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
-  const float r = fmaf(-poly, __expf(-ax * ax), 1.0f);
-  return copysignf(r, x);
+  const float r = fmaf(-poly, ex2_approx(-zc * zc), 1.0f);  // erf(|v| / sqrt 2)
+  const float hv = 0.5f * v;
+  return fmaf(hv, copysignf(r, v), hv);
 }
-__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erf_as(v * 0.70710678118654752f)); }
 
 // tmA: A [M,K], box {64,128};  tmB: W [N,K], box {64,128} (half a weight slab);  tmC: out [M,N] fp16, box {64,128}
 template <int EPI, int STAGES>
@@ -342,7 +343,7 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
       for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
-        mbar_wait_cluster(&tempty_bar[as], aph ^ 1);
+        mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * GEMM_BN;
         for (int kb = 0; kb < KB; ++kb) {
@@ -412,7 +413,7 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (sl == COLS_PER_THREAD / 64 - 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(tempty_leader0 + as * 8);  // the leader's MMA thread owns the pair's TMEM
+          if (lane == 0) mbar_arrive_remote(tempty_leader0 + as * 8);  // the leader's MMA thread owns the pair's TMEM
         }
         fence_proxy_async_smem();
         named_bar_sync(2 + split, 128);

@@ -80,6 +80,11 @@ __device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.ac
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {  // possibly remote barrier
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// arrive on a (possibly remote) barrier of the cluster with the default cta-scope release: no cluster-wide memory
+// fence — for pure "resource is free" signals that publish no memory (the .release.cluster form costs a MEMBAR)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {  // local barrier, cluster-scope acquire
   uint32_t ok = 0;
   while (!ok) {
