@@ -33,6 +33,15 @@ METRIC = "poses/sec (H=20,K=10,F=243)"
 C, J = 512, 17
 
 
+def workload_config(world):
+    F, B, H, K = F_FRAMES, B_CLIPS, H_PER_GPU, K_STEPS
+    return {"workload": f"c3: F={F} J=17 C=512 depth=8, B={B} clips, H={H}/GPU (H_total={H * world}), K={K}, "
+                        f"flip-TTA, Philox noise in-kernel, JPMA (J-Agg+P-Agg) included",
+            "parallelism": f"hypothesis-sharded x{world}, one NCCL all-gather" if world > 1 else "single GPU",
+            "l2": "activation working set 4.6 GB per step >> 126 MB L2 (no flush needed)",
+            "unit_definition": "pose = one output frame at H=20,K=10: B*F*(H_total/20) per step"}
+
+
 def f_tok(F):
     """Algorithmic FLOPs per token per denoiser forward (SURVEY §8d / BASELINE.md §3)."""
     return 256 * C * C + 8 * 4 * J * C + 8 * 4 * F * C + 10 * C + 6 * C
@@ -146,7 +155,7 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "poses/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"F={F_FRAMES} J=17 C=512 B={B_CLIPS} H={H_PER_GPU} K={K_STEPS} flip-TTA (bounded sample)"},
+        "config": workload_config(max(args.gpus, 1)),
         "cpu_baseline": {"value": value, "unit": "poses/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -192,7 +201,9 @@ def kernel_rooflines(eng, T, n_streams, peaks):
             kw["ln_b"] = (ones, zeros, 1e-6)
         t = timeit(lambda: eng.test_gemm(mode, a, w, bias, F=eng.frames, **kw))
         fl = 2.0 * T * w.shape[0] * w.shape[1]
-        res[name] = {"ms": t * 1e3, "tflops": fl / t / 1e12, "frac_tensor": fl / t / 1e12 / peaks["tflops"]}
+        byt = KERNEL_MODEL[name][0] * T
+        res[name] = {"ms": t * 1e3, "tflops": fl / t / 1e12, "frac_tensor": fl / t / 1e12 / peaks["tflops"],
+                     "gbs": byt / t / 1e9, "frac_hbm": byt / t / 1e9 / peaks["hbm_gbs"]}
     qkv = torch.cat([a512, a512, a512], dim=1).contiguous()
     for name, temporal in (("attn_temporal", True), ("attn_spatial", False)):
         t = timeit(lambda: eng.test_attn(temporal, qkv, n_streams))
@@ -202,6 +213,27 @@ def kernel_rooflines(eng, T, n_streams, peaks):
         res[name] = {"ms": t * 1e3, "tflops": fl / t / 1e12, "frac_tensor": fl / t / 1e12 / peaks["tflops"],
                      "gbs": byt / t / 1e9, "frac_hbm": byt / t / 1e9 / peaks["hbm_gbs"]}
     return res
+
+
+# algorithmic HBM bytes per token of each kernel and the resource that bounds it
+KERNEL_MODEL = {"gemm_qkv": (4096, "tensor"), "gemm_fc1_gelu": (3072, "tensor"), "gemm_proj_res_ln": (6144, "hbm"),
+                "gemm_fc2_res_ln2": (7168, "hbm"), "attn_temporal": (4096, "hbm"), "attn_spatial": (4096, "hbm")}
+# DRAM bytes per launch measured with ncu (dram__bytes_read.sum + dram__bytes_write.sum, T = 660 960; profiles/)
+NCU_TRAFFIC = {"gemm_qkv": 2.65e9, "gemm_fc1_gelu": 1.97e9, "gemm_proj_res_ln": 4.0e9, "gemm_fc2_res_ln2": 4.68e9,
+               "attn_temporal": 2.68e9, "attn_spatial": 2.68e9}
+
+
+def roofline_of(name, k, flops, T, peaks):
+    byt, bound = KERNEL_MODEL[name]
+    traffic = NCU_TRAFFIC[name] if T == 2 * B_CLIPS * H_PER_GPU * J * F_FRAMES else None
+    if bound == "hbm":
+        ach = byt * T / (k["ms"] * 1e-3) / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "bytes_per_launch": byt * T,
+                "peak_source": peaks["source"] + ", copy bandwidth"}
+    return {"kernel": name, "bound": "tensor", "achieved": k["tflops"], "peak": peaks["tflops"], "unit": "TFLOP/s",
+            "frac": k["tflops"] / peaks["tflops"], "traffic": traffic, "flops_per_launch": flops,
+            "peak_source": peaks["source"] + ", burst bf16"}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -307,11 +339,7 @@ def run_ours(args, rank, world, local_rank):
         "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "fp16 operands, fp32 accumulate/residual/LN/softmax",
         "data": "synthetic",
-        "config": {"workload": f"c3: F={F} J=17 C=512 depth=8, B={B} clips, H={H}/GPU (H_total={H_total}), K={K}, "
-                               f"flip-TTA, Philox noise in-kernel, JPMA (J-Agg+P-Agg) included",
-                   "parallelism": f"hypothesis-sharded x{world}, one NCCL all-gather" if world > 1 else "single GPU",
-                   "l2": "activation working set 6.5 GB per step >> 126 MB L2 (no flush needed)",
-                   "unit_definition": "pose = one output frame at H=20,K=10: B*F*(H_total/20) per step"},
+        "config": workload_config(world),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": t_e2e / args.steps * 1e3,
@@ -319,9 +347,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": launches_per_call * args.steps,
         "sampler_tflops": flops / t_total / 1e12 / world,
         "sampler_frac_of_sustained_peak": flops / t_total / 1e12 / world / peaks["tflops_sustained"],
-        "roofline": {"kernel": dom, "bound": "tensor", "achieved": kern[dom]["tflops"], "peak": peaks["tflops"],
-                     "unit": "TFLOP/s", "frac": kern[dom]["tflops"] / peaks["tflops"], "traffic": None,
-                     "flops_per_launch": dom_flops, "peak_source": peaks["source"] + ", burst bf16"},
+        "roofline": roofline_of(dom, kern[dom], dom_flops, T, peaks),
         "kernels": kern,
     }
     if cpu_line:
@@ -344,9 +370,11 @@ def main():
         run_reference_arm(args, rank)
         return
     if world > 1:
+        import torch
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
         run_ours(args, rank, world, local_rank)
     finally:
