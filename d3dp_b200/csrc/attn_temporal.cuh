@@ -255,3 +255,182 @@ attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParam
 }
 
 }  // namespace d3dp
+
+// =====================================================================================================================
+// Long-sequence variant, 256 < F <= 384 (the sweep's F = 351): one item = (sequence, head) as above, but the score row
+// no longer fits one UMMA N tile, so S is produced by two MMAs of N = rows/2 each into adjacent TMEM columns
+// [0, rows), P (fp16) overwrites [0, rows/2), O lives at [384, 448).  One shared-memory stage (3 x 48 KB), the up to
+// three 128-row query tiles of an item are processed one after the other by a single softmax warpgroup.  Coverage of
+// BASELINE config 5, not a tuned kernel.
+namespace d3dp {
+
+constexpr int ATTL_TILE_BYTES = 384 * 128;
+constexpr int ATTL_SMEM_BYTES = 3 * ATTL_TILE_BYTES + 256 + 1024;
+
+__global__ void __launch_bounds__(192, 1)
+attn_temporal_long_kernel(const __grid_constant__ CUtensorMap tmQKV /* box {64, rows/2} */, const AttnTParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 3 * ATTL_TILE_BYTES);
+  uint64_t* empty_bar = full_bar + 1;
+  uint64_t* sfull_bar = empty_bar + 1;
+  uint64_t* pfull_bar = sfull_bar + 1;
+  uint64_t* ofull_bar = pfull_bar + 1;
+  uint64_t* sfree_bar = ofull_bar + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sfree_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_items = p.num_seq * 8;
+  const int n_mtiles = (p.F + 127) / 128;
+  const int half = p.rows / 2;  // rows per TMA box and per S MMA (multiple of 16)
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(full_bar, 1);
+    mbar_init(empty_bar, 1);
+    mbar_init(sfull_bar, 1);
+    mbar_init(pfull_bar, 4);
+    mbar_init(ofull_bar, 1);
+    mbar_init(sfree_bar, 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t ph = 0;
+      const uint32_t bytes = 3u * p.rows * 128u;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int seq = item >> 3, head = item & 7;
+        mbar_wait(empty_bar, ph ^ 1);
+        mbar_expect_tx(full_bar, bytes);
+        const int row0 = seq * p.F;
+        for (int t3 = 0; t3 < 3; ++t3)
+          for (int hb = 0; hb < 2; ++hb)
+            tma_load_2d(smem + t3 * ATTL_TILE_BYTES + hb * half * 128, &tmQKV, full_bar, t3 * 512 + head * 64,
+                        row0 + hb * half);
+        ph ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(128, half, 0, 0);
+      const uint32_t idesc_o = make_idesc_f16(128, 64, 0, 1);
+      const int pv_ksteps = p.rows / 16;
+      uint32_t ph = 0, uph = 0;  // uph: phase of the per-query-tile barriers (one use per query tile)
+      const uint32_t q_base = smem_u32(smem), k_base = q_base + ATTL_TILE_BYTES, v_base = q_base + 2 * ATTL_TILE_BYTES;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        mbar_wait(full_bar, ph);
+        tc_fence_after();
+        for (int mt = 0; mt < n_mtiles; ++mt) {
+          mbar_wait(sfree_bar, uph ^ 1);
+          tc_fence_after();
+          for (int hb = 0; hb < 2; ++hb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_f16_ss(tmem_base + hb * half, make_sdesc_sw128(q_base + mt * 128 * 128 + k * 32, 16, 1024),
+                         make_sdesc_sw128(k_base + hb * half * 128 + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+          tc_commit(sfull_bar);
+          mbar_wait(pfull_bar, uph);
+          tc_fence_after();
+          for (int k = 0; k < pv_ksteps; ++k)
+            mma_f16_ts(tmem_base + 384, tmem_base + k * 8, make_sdesc_sw128(v_base + k * 16 * 128, 1024, 1024), idesc_o,
+                       k != 0 ? 1u : 0u);
+          tc_commit(ofull_bar);
+          uph ^= 1;
+        }
+        tc_commit(empty_bar);
+        ph ^= 1;
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const int nchunks = (p.rows + 31) / 32;
+    const int full_chunks = p.F >> 5, tail = p.F & 31;
+    uint32_t uph = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int seq = item >> 3, head = item & 7;
+      for (int mt = 0; mt < n_mtiles; ++mt) {
+        const int qrow = mt * 128 + r;
+        mbar_wait(sfull_bar, uph);
+        tc_fence_after();
+        float mx = -INFINITY;
+        for (int c = 0; c < nchunks; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_s + c * 32, v);
+          tmem_ld_wait();
+          const int nv = c < full_chunks ? 32 : (c == full_chunks ? tail : 0);
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < nv) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+        const float moff = mx * p.scale_log2e;
+        float sum = 0.f;
+        for (int c = 0; c < nchunks; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_s + c * 32, v);
+          tmem_ld_wait();
+          const int nv = c < full_chunks ? 32 : (c == full_chunks ? tail : 0);
+          uint32_t o[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float a = 2 * i < nv ? ex2_approx(fmaf(__uint_as_float(v[2 * i]), p.scale_log2e, -moff)) : 0.f;
+            const float b = 2 * i + 1 < nv ? ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2e, -moff)) : 0.f;
+            sum += a + b;
+            o[i] = pack_half2(a, b);
+          }
+          tmem_st16(t_s + c * 16, o);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pfull_bar);
+        mbar_wait(ofull_bar, uph);
+        tc_fence_after();
+        const float inv = 1.0f / sum;
+        __half* orow = p.out + (static_cast<size_t>(seq) * p.F + qrow) * 512 + head * 64;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_s + 384 + c * 32, v);
+          tmem_ld_wait();
+          if (qrow < p.F) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const uint32_t* u = v + 16 * i;
+              stg256(orow + c * 32 + 16 * i, pack_half2(__uint_as_float(u[0]) * inv, __uint_as_float(u[1]) * inv),
+                     pack_half2(__uint_as_float(u[2]) * inv, __uint_as_float(u[3]) * inv),
+                     pack_half2(__uint_as_float(u[4]) * inv, __uint_as_float(u[5]) * inv),
+                     pack_half2(__uint_as_float(u[6]) * inv, __uint_as_float(u[7]) * inv),
+                     pack_half2(__uint_as_float(u[8]) * inv, __uint_as_float(u[9]) * inv),
+                     pack_half2(__uint_as_float(u[10]) * inv, __uint_as_float(u[11]) * inv),
+                     pack_half2(__uint_as_float(u[12]) * inv, __uint_as_float(u[13]) * inv),
+                     pack_half2(__uint_as_float(u[14]) * inv, __uint_as_float(u[15]) * inv));
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sfree_bar);
+        uph ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace d3dp

@@ -210,6 +210,7 @@ int ensure_attrs(d3dp_handle* h) {
   if ((rc = set_smem_attr(h, k_gemm_proj, kSmemN512))) return rc;
   if ((rc = set_smem_attr(h, k_gemm_fc2, kSmemN512))) return rc;
   if ((rc = set_smem_attr(h, attn_temporal_kernel, ATT_SMEM_BYTES))) return rc;
+  if ((rc = set_smem_attr(h, attn_temporal_long_kernel, ATTL_SMEM_BYTES))) return rc;
   if ((rc = set_smem_attr(h, attn_spatial_kernel, SP_SMEM_BYTES))) return rc;
   h->attrs_set = true;
   return D3DP_OK;
@@ -263,20 +264,22 @@ int launch_gemm(d3dp_handle* h, int mode, const CUtensorMap& tmA, const CUtensor
 
 int launch_attn_temporal(d3dp_handle* h, const __half* qkv, __half* o16, int n_streams, cudaStream_t st) {
   const int F = h->cfg.frames;
-  if (F > 256) return fail(h, D3DP_E_INVALID, "temporal attention: frames > 256 not supported in this build");
+  if (F > 384) return fail(h, D3DP_E_INVALID, "temporal attention: frames > 384 not supported in this build");
   const long long T = static_cast<long long>(n_streams) * kJ * F;
   AttnTParams p;
   p.num_seq = n_streams * kJ;
   p.F = F;
-  p.rows = (F + 15) / 16 * 16;
+  p.rows = F <= 256 ? (F + 15) / 16 * 16 : (F + 31) / 32 * 32;  // long kernel: two halves, each a multiple of 16
   p.out = o16;
   p.scale_log2e = 0.125f * 1.4426950408889634f;
   CUtensorMap tm;
-  int rc = make_tmap(h, &tm, qkv, static_cast<uint64_t>(T), 1536, static_cast<uint32_t>(p.rows));
+  const bool is_long = F > 256;
+  int rc = make_tmap(h, &tm, qkv, static_cast<uint64_t>(T), 1536, static_cast<uint32_t>(is_long ? p.rows / 2 : p.rows));
   if (rc) return rc;
   const int items = p.num_seq * 8;
   const int grid = items < h->num_sms ? items : h->num_sms;
-  attn_temporal_kernel<<<grid, 320, ATT_SMEM_BYTES, st>>>(tm, p);
+  if (is_long) attn_temporal_long_kernel<<<grid, 192, ATTL_SMEM_BYTES, st>>>(tm, p);
+  else attn_temporal_kernel<<<grid, 320, ATT_SMEM_BYTES, st>>>(tm, p);
   CK(cudaGetLastError());
   return D3DP_OK;
 }
@@ -456,7 +459,7 @@ int d3dp_create(const d3dp_config* cfg, d3dp_handle** out) {
   if (!cfg || !out) return D3DP_E_INVALID;
   *out = nullptr;
   if (cfg->joints != 17 || cfg->channels != 512 || cfg->heads != 8 || cfg->mlp_hidden != 1024 ||
-      cfg->depth < 1 || cfg->depth > 8 || cfg->frames < 1 || cfg->frames > 256 || cfg->num_timesteps < 1)
+      cfg->depth < 1 || cfg->depth > 8 || cfg->frames < 1 || cfg->frames > 384 || cfg->num_timesteps < 1)
     return D3DP_E_INVALID;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return D3DP_E_CUDA;

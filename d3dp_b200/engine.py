@@ -40,7 +40,7 @@ class Engine:
         with torch.cuda.device(self.device):
             rc = self.lib.d3dp_create(C.byref(cfg), C.byref(self.handle))
         if rc != 0:
-            raise D3dpError(f"d3dp_create failed (code {rc}): needs an sm_100 GPU, C=512, F<=256, depth<=8")
+            raise D3dpError(f"d3dp_create failed (code {rc}): needs an sm_100 GPU, C=512, F<=384, depth<=8")
         self._ws = None
         self._keep = []
 

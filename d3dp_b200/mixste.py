@@ -45,8 +45,8 @@ class MixSTE2(nn.Module):
                 (17, 2, 512, 8, 2.0, True, None):
             raise ValueError("d3dp_b200 implements the D3DP configuration of MixSTE2 only: 17 joints, 2 input "
                              "channels, embed_dim_ratio=512, 8 heads, mlp_ratio=2, qkv_bias=True, qk_scale=None")
-        if not 1 <= depth <= 8 or not 1 <= num_frame <= 256:
-            raise ValueError("d3dp_b200 supports depth 1..8 and 1..256 frames in this build")
+        if not 1 <= depth <= 8 or not 1 <= num_frame <= 384:
+            raise ValueError("d3dp_b200 supports depth 1..8 and 1..384 frames in this build")
         norm_layer = norm_layer or partial(nn.LayerNorm, eps=1e-6)
         C = embed_dim_ratio
         self.is_train = is_train

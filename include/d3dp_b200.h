@@ -38,7 +38,7 @@ typedef struct d3dp_handle d3dp_handle;
 /* Mirrors what D3DP.__init__ reads from `args` plus the fixed MixSTE2 hyper-parameters
  * (common/diffusionpose.py:60-88,125-126; common/arguments.py:49,50,58,101,102). */
 typedef struct d3dp_config {
-  int32_t frames;         /* args.number_of_frames (F), 1..256 in this build                      */
+  int32_t frames;         /* args.number_of_frames (F), 1..384 in this build                      */
   int32_t joints;         /* 17                                                                   */
   int32_t channels;       /* args.cs, must be 512                                                 */
   int32_t depth;          /* args.dep, 1..8                                                       */

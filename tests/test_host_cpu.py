@@ -82,7 +82,7 @@ def test_unsupported_configurations_raise():
     with pytest.raises(ValueError):
         MixSTE2(num_frame=27, embed_dim_ratio=256, depth=8)
     with pytest.raises(ValueError):
-        MixSTE2(num_frame=351, embed_dim_ratio=512, depth=8)
+        MixSTE2(num_frame=385, embed_dim_ratio=512, depth=8)
 
 
 def test_flip_permutation_and_synthetic_determinism():

@@ -78,7 +78,7 @@ def _attn_ref(qkv, groups):
     return out
 
 
-@pytest.mark.parametrize("F,S", [(27, 3), (243, 2), (81, 2), (16, 1), (200, 1)])
+@pytest.mark.parametrize("F,S", [(27, 3), (243, 2), (81, 2), (16, 1), (200, 1), (351, 1), (257, 1), (384, 1)])
 def test_attention_temporal(F, S):
     eng = _engine(F)
     g = torch.Generator().manual_seed(F)

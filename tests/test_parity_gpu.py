@@ -40,7 +40,7 @@ def test_denoiser_forward_matches_reference_golden():
     assert mean <= MEAN_TOL and mx <= MAX_TOL
 
 
-@pytest.mark.parametrize("F,B,H,K,wseed", [(27, 1, 2, 2, 7), (81, 1, 1, 2, 3), (16, 2, 1, 3, 11)])
+@pytest.mark.parametrize("F,B,H,K,wseed", [(27, 1, 2, 2, 7), (81, 1, 1, 2, 3), (16, 2, 1, 3, 11), (351, 1, 1, 2, 5)])
 def test_sampler_matches_oracle_fresh_seeds(F, B, H, K, wseed):
     from d3dp_b200.synthetic import synthetic_inputs, synthetic_pose_estimator_state
     from oracle import d3dp_oracle as orc
