@@ -182,7 +182,7 @@ int set_smem_attr(d3dp_handle* h, KernelT k, int bytes) {
 constexpr int kStagesN256 = 3;
 auto* const k_gemm_qkv = gemm_tcgen05_kernel<EPI_BIAS_F16, kStagesN256>;
 auto* const k_gemm_fc1 = gemm_tcgen05_kernel<EPI_BIAS_GELU_F16, kStagesN256>;
-constexpr int kLnStages = 3, kLnRing = 2;
+constexpr int kLnStages = 2, kLnRing = 2;
 auto* const k_gemm_proj = gemm_ln_pair_kernel<EPI_RES_LN, kLnStages, kLnRing>;
 auto* const k_gemm_fc2 = gemm_ln_pair_kernel<EPI_RES_LN2, kLnStages, kLnRing>;
 constexpr int kSmemN256 = GemmSmem<kStagesN256>::TOTAL;
@@ -227,9 +227,11 @@ int launch_gemm(d3dp_handle* h, int mode, const CUtensorMap& tmA, const CUtensor
     if (rc) return rc;
   }
   CUtensorMap tmA64 = tmA;  // LN modes: 64-row boxes (each CTA of the pair fetches half of the A tile and multicasts)
+  CUtensorMap tmO = tmA;    // LN modes: LayerNorm output a16 [M,512] (TMA store)
   if (mode == EPI_RES_LN || mode == EPI_RES_LN2) {
     int rc = make_tmap(h, &tmA64, p.a_ptr, p.M, p.K, 64);
     if (rc) return rc;
+    if (p.out16 && (rc = make_tmap(h, &tmO, p.out16, p.M, 512, 128))) return rc;
   }
   const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int bn = (mode == EPI_BIAS_F16 || mode == EPI_BIAS_GELU_F16) ? 256 : 512;
@@ -252,8 +254,8 @@ int launch_gemm(d3dp_handle* h, int mode, const CUtensorMap& tmA, const CUtensor
     case EPI_RES_LN:
     case EPI_RES_LN2: {
       const int pairs = tiles_m < h->num_sms / 2 ? tiles_m : h->num_sms / 2;  // one CTA pair (cluster) per M tile
-      if (mode == EPI_RES_LN) k_gemm_proj<<<2 * pairs, 352, kSmemN512, st>>>(tmA64, tmB, tmC, p);
-      else k_gemm_fc2<<<2 * pairs, 352, kSmemN512, st>>>(tmA64, tmB, tmC, p);
+      if (mode == EPI_RES_LN) k_gemm_proj<<<2 * pairs, 352, kSmemN512, st>>>(tmA64, tmB, tmC, tmO, p);
+      else k_gemm_fc2<<<2 * pairs, 352, kSmemN512, st>>>(tmA64, tmB, tmC, tmO, p);
       break;
     }
     default: return fail(h, D3DP_E_INVALID, "gemm: bad mode");

@@ -11,7 +11,9 @@
 // lane quadrant, so only the eight warps that share rows wait for each other.
 // The residual tile is streamed by TMA into a small swizzled ring (no uncoalesced row-per-thread global loads), the
 // A tile both CTAs need is fetched once (each CTA loads half of its rows and multicasts them to the pair);
-// outputs leave with 256-bit stores, one full 32 B sector per lane.  (An L2 prefetch of the next tile's x was
+// outputs are staged in swizzled smem and leave by TMA store (row-per-thread 256-bit global stores cost one L1
+// wavefront per 32 B sector: ~5 us per tile, measured).  Two operand stages suffice: the kernel is epilogue-bound
+// (3 vs 2 stages and L2 prefetch distances 0..16 k-blocks all measure the same), which pays for the staging buffers.  (An L2 prefetch of the next tile's x was
 // measured to cost ~0.9 GB of extra DRAM reads per launch — lines evicted before use — and was removed.)
 //
 //   EPI_RES_LN   x += A.W^T + b ; a16 = fp16(LN_a(x))
@@ -26,7 +28,8 @@ struct LnPairSmem {
   static constexpr int A_BYTES = 128 * 64 * 2;
   static constexpr int B_BYTES = 256 * 64 * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;             // 48 KB
-  static constexpr int RING_OFFSET = STAGES * STAGE_BYTES;          // [2 groups][RING] x 16 KB residual chunks
+  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;           // [2 groups] x 16 KB output staging (TMA stores)
+  static constexpr int RING_OFFSET = STG_OFFSET + 2 * 16384;        // [2 groups][RING] x 16 KB residual chunks
   static constexpr int SLOT_BYTES = 128 * 32 * 4;
   static constexpr int BAR_OFFSET = RING_OFFSET + 2 * RING * SLOT_BYTES;
   // barriers: full[STAGES] empty[STAGES] tfull[2] tempty[2] rfull[2][RING] rempty[2][RING] xch[2] ; tmem ptr
@@ -38,7 +41,10 @@ struct LnPairSmem {
 template <int EPI, int STAGES, int RING>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1)
 gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmO,
+                    const GemmParams p) {
+  // tmA: A [M,K] fp16 box {64,64}; tmB: W [512,K] fp16 box {64,256}; tmX: x [M,512] fp32 box {32,128} (residual loads
+  // and x stores); tmO: a16 [M,512] fp16 box {64,128} (LayerNorm output stores)
   using L = LnPairSmem<STAGES, RING>;
   static_assert(EPI == EPI_RES_LN || EPI == EPI_RES_LN2, "LN epilogues only");
   extern __shared__ uint8_t smem_raw[];
@@ -68,6 +74,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmO);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 2);  // the A half this CTA multicasts lands in both CTAs: both MMAs must be done
@@ -171,6 +178,40 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int qd = rank * 2 + g;      // quarter index of this thread's columns within the 512-wide row
     int as = 0, rslot = 0, xn = 0;
     uint32_t aph = 0, rph = 0;
+    // Outputs are staged per group in one 16 KB 128B-swizzled buffer (conflict-free for one-row-per-thread 16 B
+    // writes) and leave by TMA store: a 32-column fp32 chunk of x or a 64-column fp16 slab of a16 at a time.
+    uint8_t* stg = smem + L::STG_OFFSET + g * 16384 + r * 128;
+    const bool leader = (ew & 3) == 0 && lane == 0;
+    auto stage_begin = [&]() {  // the previous store of this group has finished reading the buffer
+      if (leader) tma_store_wait_read<0>();
+      named_bar_sync(2 + g, 128);
+    };
+    auto stage_x_chunk = [&](const uint32_t (&v)[32], int c, int tile) {
+      stage_begin();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(stg + ((j ^ (r & 7)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      fence_proxy_async_smem();
+      named_bar_sync(2 + g, 128);
+      if (leader) {
+        tma_store_2d(&tmX, stg - r * 128, ncol0 + lcol0 + c * 32, tile * 128);
+        tma_store_commit();
+      }
+    };
+    auto stage_a_half = [&](const uint32_t (&o)[16], int c) {  // 32 fp16 columns = half of a 64-column slab
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(stg + ((((c & 1) * 4 + j) ^ (r & 7)) << 4)) =
+            make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    };
+    auto stage_a_store = [&](int c, int tile) {  // after the odd chunk of a slab
+      fence_proxy_async_smem();
+      named_bar_sync(2 + g, 128);
+      if (leader) {
+        tma_store_2d(&tmO, stg - r * 128, ncol0 + lcol0 + (c - 1) * 32, tile * 128);
+        tma_store_commit();
+      }
+    };
 
     // publish this row-quarter's (mean, M2) to both CTAs, wait for the four quarters of the row, return mean / rstd
     auto exchange = [&](float m_loc, float m2_loc, float eps, float& mean, float& rstd) {
@@ -203,8 +244,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = cluster_id; tile < tiles_m; tile += num_clusters) {
       const int grow = tile * 128 + r;
       const bool valid = grow < p.M;
-      float* xrow = p.x + static_cast<size_t>(grow) * 512 + ncol0 + lcol0;
-      __half* arow = p.out16 ? p.out16 + static_cast<size_t>(grow) * 512 + ncol0 + lcol0 : nullptr;
+      const bool write_a = p.out16 != nullptr;
       const int f = valid ? (grow % p.F) : 0;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
@@ -241,14 +281,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           v[i] = __float_as_uint(t);
         }
         tmem_st32(taddr + c * 32, v);
-        if constexpr (EPI == EPI_RES_LN) {
-          if (valid) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              stg256(xrow + c * 32 + 8 * i, v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3], v[8 * i + 4],
-                     v[8 * i + 5], v[8 * i + 6], v[8 * i + 7]);
-          }
-        }
+        if constexpr (EPI == EPI_RES_LN) stage_x_chunk(v, c, tile);
       }
       tmem_st_wait();
       const float m_loc = pv + s1 * (1.0f / 128.0f);
@@ -276,27 +309,17 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           v[i] = __float_as_uint(y);
         }
         if constexpr (EPI == EPI_RES_LN) {
-          if (valid && arow) {
+          if (write_a) {
+            uint32_t o[16];
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
-              stg256(arow + c * 32 + 16 * i,
-                     pack_half2(__uint_as_float(v[16 * i]), __uint_as_float(v[16 * i + 1])),
-                     pack_half2(__uint_as_float(v[16 * i + 2]), __uint_as_float(v[16 * i + 3])),
-                     pack_half2(__uint_as_float(v[16 * i + 4]), __uint_as_float(v[16 * i + 5])),
-                     pack_half2(__uint_as_float(v[16 * i + 6]), __uint_as_float(v[16 * i + 7])),
-                     pack_half2(__uint_as_float(v[16 * i + 8]), __uint_as_float(v[16 * i + 9])),
-                     pack_half2(__uint_as_float(v[16 * i + 10]), __uint_as_float(v[16 * i + 11])),
-                     pack_half2(__uint_as_float(v[16 * i + 12]), __uint_as_float(v[16 * i + 13])),
-                     pack_half2(__uint_as_float(v[16 * i + 14]), __uint_as_float(v[16 * i + 15])));
+            for (int i = 0; i < 16; ++i) o[i] = pack_half2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+            if ((c & 1) == 0) stage_begin();
+            stage_a_half(o, c);
+            if (c & 1) stage_a_store(c, tile);
           }
         } else {
           if (has_b) tmem_st32(taddr + c * 32, v);
-          if (valid) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              stg256(xrow + c * 32 + 8 * i, v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3], v[8 * i + 4],
-                     v[8 * i + 5], v[8 * i + 6], v[8 * i + 7]);
-          }
+          stage_x_chunk(v, c, tile);
         }
       }
       if constexpr (EPI == EPI_RES_LN2) {
@@ -320,11 +343,10 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                               sprm[1024 + n + 2 * i + 1];
               o[i] = pack_half2(a, b);
             }
-            if (valid && arow) {
-#pragma unroll
-              for (int i = 0; i < 2; ++i)
-                stg256(arow + c * 32 + 16 * i, o[8 * i], o[8 * i + 1], o[8 * i + 2], o[8 * i + 3], o[8 * i + 4],
-                       o[8 * i + 5], o[8 * i + 6], o[8 * i + 7]);
+            if (write_a) {
+              if ((c & 1) == 0) stage_begin();
+              stage_a_half(o, c);
+              if (c & 1) stage_a_store(c, tile);
             }
           }
         }
@@ -337,6 +359,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   }
 
+  tma_store_wait_all<0>();  // no-op for threads that issued no bulk stores
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // the peer may still be reading / writing this CTA's exchange buffers
