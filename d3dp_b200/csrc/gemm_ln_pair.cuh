@@ -290,11 +290,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       exchange(m_loc, m2_loc, p.ln_a_eps, mean, rstd);
       // ---- pass 2: y = LN_a(v) ; LN2: shifted sums of y for the second LayerNorm
       float t1 = 0.f, t2 = 0.f, py = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c * 32, v);
-        tmem_ld_wait();
+      auto ln_a_chunk = [&](uint32_t (&v)[32], int c) {
         const int n = lcol0 + c * 32;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -321,6 +317,19 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (has_b) tmem_st32(taddr + c * 32, v);
           stage_x_chunk(v, c, tile);
         }
+      };
+      {  // software-pipelined TMEM reads: chunk c+1 is in flight while chunk c is processed / staged
+        uint32_t va[32], vb[32];
+        tmem_ld32(taddr, va);
+#pragma unroll 1
+        for (int c = 0; c < 4; c += 2) {
+          tmem_ld_wait();
+          tmem_ld32(taddr + (c + 1) * 32, vb);
+          ln_a_chunk(va, c);
+          tmem_ld_wait();
+          if (c + 2 < 4) tmem_ld32(taddr + (c + 2) * 32, va);
+          ln_a_chunk(vb, c + 1);
+        }
       }
       if constexpr (EPI == EPI_RES_LN2) {
         if (has_b) {  // uniform over the grid
@@ -329,11 +338,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const float m2_loc2 = fmaxf(t2 - t1 * t1 * (1.0f / 128.0f), 0.f);
           float mean2, rstd2;
           exchange(m_loc2, m2_loc2, p.ln_b_eps, mean2, rstd2);
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            tmem_ld32(taddr + c * 32, v);
-            tmem_ld_wait();
+          auto ln_b_chunk = [&](const uint32_t (&v)[32], int c) {
             const int n = lcol0 + c * 32;
             uint32_t o[16];
 #pragma unroll
@@ -347,6 +352,19 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if ((c & 1) == 0) stage_begin();
               stage_a_half(o, c);
               if (c & 1) stage_a_store(c, tile);
+            }
+          };
+          {
+            uint32_t va[32], vb[32];
+            tmem_ld32(taddr, va);
+#pragma unroll 1
+            for (int c = 0; c < 4; c += 2) {
+              tmem_ld_wait();
+              tmem_ld32(taddr + (c + 1) * 32, vb);
+              ln_b_chunk(va, c);
+              tmem_ld_wait();
+              if (c + 2 < 4) tmem_ld32(taddr + (c + 2) * 32, va);
+              ln_b_chunk(vb, c + 1);
             }
           }
         }
