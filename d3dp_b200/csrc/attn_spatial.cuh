@@ -21,7 +21,8 @@ struct AttnSParams {
 
 constexpr int SP_J = 17;
 constexpr int SP_ROW_HALFS = 1536 + 8;  // +16 B pad: consecutive joints land 4 banks apart -> conflict-free fragments
-constexpr int SP_SMEM_BYTES = SP_J * SP_ROW_HALFS * 2;
+constexpr int SP_BUF_BYTES = SP_J * SP_ROW_HALFS * 2;
+constexpr int SP_SMEM_BYTES = 2 * SP_BUF_BYTES;  // double-buffered: the next (stream, frame) streams in during compute
 
 __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -37,24 +38,36 @@ __global__ void __launch_bounds__(256) attn_spatial_kernel(const AttnSParams p) 
   const int g = lane >> 2, t = lane & 3;
   const int num_items = p.num_streams * p.F;
 
-  for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+  // gather the 17 qkv rows of one (stream, frame) into buffer `buf`: row(j) = (s*17 + j)*F + f
+  auto prefetch = [&](int item, int buf) {
     const int s = item / p.F, f = item % p.F;
-    // gather the 17 qkv rows of this (stream, frame): row(j) = (s*17 + j)*F + f
-    __syncthreads();  // previous item fully consumed
+    __half* dstb = sm + buf * (SP_BUF_BYTES / 2);
     for (int idx = threadIdx.x; idx < SP_J * 192; idx += blockDim.x) {
       const int j = idx / 192, ch = idx % 192;  // 192 x 16 B per row
       const __half* src = p.qkv + (static_cast<size_t>(s * SP_J + j) * p.F + f) * 1536 + ch * 8;
-      const uint32_t dst = smem_u32(sm + j * SP_ROW_HALFS + ch * 8);
+      const uint32_t dst = smem_u32(dstb + j * SP_ROW_HALFS + ch * 8);
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  };
+  int buf = 0;
+  if (blockIdx.x < num_items) prefetch(blockIdx.x, 0);
+  for (int item = blockIdx.x; item < num_items; item += gridDim.x, buf ^= 1) {
+    const int s = item / p.F, f = item % p.F;
+    __syncthreads();  // everyone is done with the other buffer (previous item)
+    if (item + gridDim.x < num_items) {
+      prefetch(item + gridDim.x, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     __syncthreads();
+    __half* cur = sm + buf * (SP_BUF_BYTES / 2);
 
     const int h = warp;
-    const __half* Q = sm + h * 64;
-    const __half* K = sm + 512 + h * 64;
-    const __half* V = sm + 1024 + h * 64;
+    __half* Q = cur + h * 64;
+    const __half* K = cur + 512 + h * 64;
+    const __half* V = cur + 1024 + h * 64;
     auto ld32 = [&](const __half* base, int row, int col) -> uint32_t {
       return row < SP_J ? *reinterpret_cast<const uint32_t*>(base + row * SP_ROW_HALFS + col) : 0u;
     };
@@ -156,20 +169,20 @@ __global__ void __launch_bounds__(256) attn_spatial_kernel(const AttnSParams p) 
         mma_16816(oacc[1][nt], pa[1][1], b0, 0u);
       }
     }
-    // ---- store: row g / g+8 of m-tile 0 (joints 0-15), row g of m-tile 1 only for joint 16
+    // ---- store: stage the head's 17 x 64 outputs in the warp's own (now dead) Q slice, then write 16 B per lane
+    __syncwarp();
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const int col = h * 64 + nt * 8 + 2 * t;
-      {
-        const size_t r0 = (static_cast<size_t>(s * SP_J + g) * p.F + f) * 512;
-        const size_t r1 = (static_cast<size_t>(s * SP_J + g + 8) * p.F + f) * 512;
-        *reinterpret_cast<uint32_t*>(p.out + r0 + col) = pack_half2(oacc[0][nt][0], oacc[0][nt][1]);
-        *reinterpret_cast<uint32_t*>(p.out + r1 + col) = pack_half2(oacc[0][nt][2], oacc[0][nt][3]);
-      }
-      if (g == 0) {
-        const size_t r2 = (static_cast<size_t>(s * SP_J + 16) * p.F + f) * 512;
-        *reinterpret_cast<uint32_t*>(p.out + r2 + col) = pack_half2(oacc[1][nt][0], oacc[1][nt][1]);
-      }
+      const int col = nt * 8 + 2 * t;
+      *reinterpret_cast<uint32_t*>(Q + g * SP_ROW_HALFS + col) = pack_half2(oacc[0][nt][0], oacc[0][nt][1]);
+      *reinterpret_cast<uint32_t*>(Q + (g + 8) * SP_ROW_HALFS + col) = pack_half2(oacc[0][nt][2], oacc[0][nt][3]);
+      if (g == 0) *reinterpret_cast<uint32_t*>(Q + 16 * SP_ROW_HALFS + col) = pack_half2(oacc[1][nt][0], oacc[1][nt][1]);
+    }
+    __syncwarp();
+    for (int idx = lane; idx < SP_J * 8; idx += 32) {
+      const int j = idx >> 3, ch = idx & 7;
+      const uint4 val = *reinterpret_cast<const uint4*>(Q + j * SP_ROW_HALFS + ch * 8);
+      *reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(s * SP_J + j) * p.F + f) * 512 + h * 64 + ch * 8) = val;
     }
   }
 }

@@ -294,7 +294,7 @@ int launch_attn_spatial(d3dp_handle* h, const __half* qkv, __half* o16, int n_st
   p.F = h->cfg.frames;
   p.scale = 0.125f;
   const int items = n_streams * p.F;
-  const int cap = h->num_sms * 2;
+  const int cap = h->num_sms * 2;  // 2 CTAs per SM (2 x 105 KB of smem)
   const int grid = items < cap ? items : cap;
   attn_spatial_kernel<<<grid, 256, SP_SMEM_BYTES, st>>>(p);
   CK(cudaGetLastError());
