@@ -6,7 +6,6 @@
 
 #include <cmath>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -179,34 +178,20 @@ int set_smem_attr(d3dp_handle* h, KernelT k, int bytes) {
 }
 
 // kernel instantiations used by the pipeline
-constexpr int kStagesN256 = 3;
-auto* const k_gemm_qkv = gemm_tcgen05_kernel<EPI_BIAS_F16, kStagesN256>;
-auto* const k_gemm_fc1 = gemm_tcgen05_kernel<EPI_BIAS_GELU_F16, kStagesN256>;
+constexpr int kGemmStages = 4;
+auto* const k_gemm_qkv = gemm_2sm_kernel<EPI_BIAS_F16, kGemmStages>;
+auto* const k_gemm_fc1 = gemm_2sm_kernel<EPI_BIAS_GELU_F16, kGemmStages>;
+constexpr int kSmemGemm = Gemm2SmSmem<kGemmStages>::TOTAL;
 constexpr int kLnStages = 2, kLnRing = 2;
 auto* const k_gemm_proj = gemm_ln_pair_kernel<EPI_RES_LN, kLnStages, kLnRing>;
 auto* const k_gemm_fc2 = gemm_ln_pair_kernel<EPI_RES_LN2, kLnStages, kLnRing>;
-constexpr int kSmemN256 = GemmSmem<kStagesN256>::TOTAL;
-constexpr int kStages2Sm = 4;
-auto* const k_gemm2_qkv = gemm_2sm_kernel<EPI_BIAS_F16, kStages2Sm>;
-auto* const k_gemm2_fc1 = gemm_2sm_kernel<EPI_BIAS_GELU_F16, kStages2Sm>;
-constexpr int kSmem2Sm = Gemm2SmSmem<kStages2Sm>::TOTAL;
-// D3DP_GEMM_1SM=1 selects the single-CTA-MMA kernel (A/B comparisons); default is the cta_group::2 kernel
-bool use_2sm() {
-  static const bool v = [] {
-    const char* e = getenv("D3DP_GEMM_1SM");
-    return !(e && e[0] == '1');
-  }();
-  return v;
-}
 constexpr int kSmemN512 = LnPairSmem<kLnStages, kLnRing>::TOTAL;
 
 int ensure_attrs(d3dp_handle* h) {
   if (h->attrs_set) return D3DP_OK;
   int rc;
-  if ((rc = set_smem_attr(h, k_gemm_qkv, kSmemN256))) return rc;
-  if ((rc = set_smem_attr(h, k_gemm_fc1, kSmemN256))) return rc;
-  if ((rc = set_smem_attr(h, k_gemm2_qkv, kSmem2Sm))) return rc;
-  if ((rc = set_smem_attr(h, k_gemm2_fc1, kSmem2Sm))) return rc;
+  if ((rc = set_smem_attr(h, k_gemm_qkv, kSmemGemm))) return rc;
+  if ((rc = set_smem_attr(h, k_gemm_fc1, kSmemGemm))) return rc;
   if ((rc = set_smem_attr(h, k_gemm_proj, kSmemN512))) return rc;
   if ((rc = set_smem_attr(h, k_gemm_fc2, kSmemN512))) return rc;
   if ((rc = set_smem_attr(h, attn_temporal_kernel, ATT_SMEM_BYTES))) return rc;
@@ -241,14 +226,8 @@ int launch_gemm(d3dp_handle* h, int mode, const CUtensorMap& tmA, const CUtensor
     case EPI_BIAS_GELU_F16: {
       const int ctiles = ((tiles_m + 1) / 2) * (p.N / bn);  // (M-tile pair, N tile) per 2-CTA cluster
       const int clusters = ctiles < h->num_sms / 2 ? ctiles : h->num_sms / 2;
-      if (use_2sm()) {
-        if (mode == EPI_BIAS_F16) k_gemm2_qkv<<<2 * clusters, GEMM_THREADS, kSmem2Sm, st>>>(tmA, tmB, tmC, p);
-        else k_gemm2_fc1<<<2 * clusters, GEMM_THREADS, kSmem2Sm, st>>>(tmA, tmB, tmC, p);
-      } else if (mode == EPI_BIAS_F16) {
-        k_gemm_qkv<<<2 * clusters, GEMM_THREADS, kSmemN256, st>>>(tmA, tmB, tmC, p);
-      } else {
-        k_gemm_fc1<<<2 * clusters, GEMM_THREADS, kSmemN256, st>>>(tmA, tmB, tmC, p);
-      }
+      if (mode == EPI_BIAS_F16) k_gemm_qkv<<<2 * clusters, GEMM_THREADS, kSmemGemm, st>>>(tmA, tmB, tmC, p);
+      else k_gemm_fc1<<<2 * clusters, GEMM_THREADS, kSmemGemm, st>>>(tmA, tmB, tmC, p);
       break;
     }
     case EPI_RES_LN:

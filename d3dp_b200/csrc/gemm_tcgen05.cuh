@@ -7,12 +7,15 @@
 // (The two residual + LayerNorm GEMMs, attn.proj and mlp.fc2, live in gemm_ln_pair.cuh.)
 //
 // A is [M,K] fp16 row-major (K-major), W is the nn.Linear weight [N,K] fp16 row-major (K-major), fp32 accumulate
-// in TMEM.  128x256 output tiles, one CTA per SM.  CTAs run as clusters of two that take vertically adjacent M
-// tiles of the same N tile: the 256x64 weight slab of every k-block is fetched once per pair (each CTA loads 128
-// rows and multicasts them), which halves the dominant L2->SM stream — at 128x256 tiles without sharing the kernel
-// is L2-bandwidth bound (measured 12.8 TB/s of L2 traffic at 56 % tensor-pipe utilisation).
-// Warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..9 = epilogue: TMEM lane == tile row, two
-// 4-warp groups of 128 columns each; fp16 results are staged in 128B-swizzled smem slabs and leave by TMA store.
+// in TMEM.  The kernel is a cta_group::2 GEMM: a CTA pair (cluster of 2) computes one 256x256 tile with a single MMA
+// stream (UMMA M=256, N=256, K=16).  Each CTA stages its own 128 A rows and HALF of the weight slab (128 of the 256
+// N rows) per k-block, so an SM reads 8 KB instead of 12 KB of operands from shared memory per MMA and fills 32 KB
+// instead of 48 KB by TMA — a single-CTA (M=128) version of this kernel measured shared-memory-bandwidth bound at
+// 56-60 % tensor-pipe utilisation; this one reaches 73 % (ncu) on the qkv shape.  The leader CTA (rank 0) issues all
+// MMAs; both CTAs' TMA loads complete on the leader's `full` barriers; MMA commits are multicast to both CTAs; each
+// CTA runs its own epilogue on its 128 rows.  Warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..9
+// = epilogue: TMEM lane == tile row, two 4-warp groups of 128 columns each; fp16 results are staged in
+// 128B-swizzled smem slabs and leave by TMA store.
 #pragma once
 #include "ptx.cuh"
 
@@ -43,19 +46,6 @@ constexpr int GEMM_BK = 64;  // 64 fp16 = one 128-byte swizzle row
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 64 + GEMM_EPI_WARPS * 32;
 
-template <int STAGES>
-struct GemmSmem {
-  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = GEMM_BN * GEMM_BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;  // full[STAGES] empty[STAGES] tfull[2] tempty[2], tmem ptr
-  static constexpr int PARAM_OFFSET = BAR_OFFSET + 256;    // bias[N], N <= 2560, staged once per launch
-  static constexpr int PARAM_FLOATS = 2560;
-  // fp16 output staged per epilogue group in two 128x64 (16 KB, 128B-swizzled) slabs for TMA stores
-  static constexpr int OUT_OFFSET = (PARAM_OFFSET + PARAM_FLOATS * 4 + 1023) / 1024 * 1024;
-  static constexpr int TOTAL = OUT_OFFSET + 2 * 2 * 16384 + 1024 /*alignment slack*/;
-};
-
 // Exact-erf GELU (reference: nn.GELU() default, common/mixste.py:24,39) with erf by Abramowitz & Stegun 7.1.26
 // (|abs error| <= 1.5e-7, far below the fp16 rounding of the result), arranged for the epilogue's issue budget:
 // branch-free, 2 MUFU (rcp, ex2) + 12 FMA-pipe ops.  With zc = v * sqrt(log2 e / 2):  erf(|v|/sqrt 2) =
@@ -74,187 +64,6 @@ __device__ __forceinline__ float gelu_erf(float v) {
 }
 
 // tmA: A [M,K], box {64,128};  tmB: W [N,K], box {64,128} (half a weight slab);  tmC: out [M,N] fp16, box {64,128}
-template <int EPI, int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-  using L = GemmSmem<STAGES>;
-  static_assert(EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16, "fp16-output epilogues only");
-  constexpr int COLS_PER_THREAD = GEMM_BN / 2;
-
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* sprm = reinterpret_cast<float*>(smem + L::PARAM_OFFSET);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int cluster_id = blockIdx.x >> 1;
-  const int num_clusters = gridDim.x >> 1;
-  const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
-  const int pairs_m = (tiles_m + 1) / 2;  // an odd last M tile is paired with an out-of-range one (TMA clips it)
-  const int tiles_n = p.N / GEMM_BN;
-  const int num_ctiles = pairs_m * tiles_n;  // cluster tiles: (M-tile pair, N tile), N fastest for A reuse in L2
-  const int KB = p.K / GEMM_BK;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmC);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 2);  // the weight half this CTA multicasts lands in both CTAs: both MMAs must be done
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], GEMM_EPI_WARPS);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<512>(tmem_ptr);
-  for (int i = threadIdx.x; i < p.N; i += blockDim.x) sprm[i] = p.bias[i];
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to it
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
-        const int m_blk = (ct / tiles_n) * 2 + rank, n_blk = ct % tiles_n;
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * L::STAGE_BYTES;
-          uint8_t* sb = sa + L::A_BYTES;
-          mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
-          // the pair shares the weight slab: each CTA fetches 128 of its 256 rows and multicasts them to both
-          tma_load_2d_mc(sb + rank * (L::B_BYTES / 2), &tmB, &full_bar[s], kb * GEMM_BK,
-                         n_blk * GEMM_BN + rank * 128, 0x3);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(128, 256, 0, 0);
-      int s = 0, as = 0;
-      uint32_t ph = 0, aph = 0;
-      for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
-        mbar_wait(&tempty_bar[as], aph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * GEMM_BN;
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + s * L::STAGE_BYTES);
-          const uint32_t b_base = a_base + L::A_BYTES;
-#pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k)
-            mma_f16_ss(d_tmem, make_sdesc_sw128(a_base + k * 32, 16, 1024), make_sdesc_sw128(b_base + k * 32, 16, 1024),
-                       idesc, (kb | k) != 0 ? 1u : 0u);
-          tc_commit_mc(&empty_bar[s], 0x3);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
-        }
-        tc_commit(&tfull_bar[as]);
-        if (++as == 2) { as = 0; aph ^= 1; }
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ epilogue
-    const int ew = warp - 2;
-    const int quad = warp & 3;         // TMEM lane quadrant this warp can address
-    const int split = ew >> 2;         // which 128-column half of the tile this thread's group owns
-    const int r = quad * 32 + lane;    // tile row == TMEM lane
-    const int col0 = split * COLS_PER_THREAD;
-    uint8_t* gbuf = smem + L::OUT_OFFSET + split * 2 * 16384;
-    const bool leader = (ew & 3) == 0 && lane == 0;
-    int as = 0;
-    uint32_t aph = 0;
-    for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
-      const int m_blk = (ct / tiles_n) * 2 + rank, n_blk = ct % tiles_n;
-      mbar_wait(&tfull_bar[as], aph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * GEMM_BN + col0;
-      // Each 4-warp group owns 128 columns = two slabs of 64; a slab is staged in smem in the 128B-swizzled layout
-      // (conflict-free for one-row-per-thread 16 B writes) and written out by one TMA store.
-      const int n0 = n_blk * GEMM_BN + col0;
-#pragma unroll 1
-      for (int sl = 0; sl < COLS_PER_THREAD / 64; ++sl) {
-        uint8_t* buf = gbuf + (sl & 1) * 16384;
-        if (leader) tma_store_wait_read<1>();  // the store that last used this buffer has drained
-        named_bar_sync(2 + split, 128);
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = sl * 2 + cc;
-          uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
-          uint32_t o[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float2 bb = *reinterpret_cast<const float2*>(sprm + n0 + c * 32 + 2 * i);
-            float a = __uint_as_float(v[2 * i]) + bb.x;
-            float b = __uint_as_float(v[2 * i + 1]) + bb.y;
-            if constexpr (EPI == EPI_BIAS_GELU_F16) {
-              a = gelu_erf(a);
-              b = gelu_erf(b);
-            }
-            o[i] = pack_half2(a, b);
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int piece = cc * 4 + i;  // 16-byte piece index inside the 128-byte slab row
-            *reinterpret_cast<uint4*>(buf + r * 128 + ((piece ^ (r & 7)) << 4)) =
-                make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-          }
-        }
-        if (sl == COLS_PER_THREAD / 64 - 1) {  // all accumulator columns of this thread are read: free the stage
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[as]);
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(2 + split, 128);
-        if (leader) {
-          tma_store_2d(&tmC, buf, n0 + sl * 64, m_blk * GEMM_BM);
-          tma_store_commit();
-        }
-      }
-      if (++as == 2) { as = 0; aph ^= 1; }
-    }
-  }
-
-  tma_store_wait_all<0>();  // no-op for threads that issued no bulk stores
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // the peer may still be multicasting into this CTA's stages
-  if (warp == 1) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
-
-}  // namespace d3dp
-
-// =====================================================================================================================
-// cta_group::2 variant: the CTA pair computes one 256x256 tile with a single MMA stream (UMMA M=256).  Each CTA stages
-// its own 128 A rows and HALF of the weight slab (128 of the 256 N rows), so per k-block an SM reads 8 KB instead of
-// 12 KB of operands from shared memory and fills 32 KB instead of 48 KB by TMA — the single-CTA kernel above is bound
-// by shared-memory bandwidth (MMA operand reads + TMA fills ~ 190 B/clk of 128).  The leader CTA (rank 0) issues all
-// MMAs; both CTAs' TMA loads complete on the leader's `full` barriers; MMA commits are multicast to both CTAs.
-namespace d3dp {
 
 template <int STAGES>
 struct Gemm2SmSmem {
