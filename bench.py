@@ -124,15 +124,16 @@ def cpu_reference_sample(repeats, warmup=0):
         return time.perf_counter() - t0
 
     # give the CPU path its best shot: eager PyTorch on many-core hosts is fastest well below the core count
-    # (oversubscribed tiny ops), so calibrate the intra-op thread count once and use the fastest
+    # (oversubscribed tiny ops), so calibrate the intra-op thread count once (one run each) and use the fastest
     ncpu = os.cpu_count() or 1
     best = None
-    for nt in sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16), min(ncpu, 8)}, reverse=True):
+    for nt in sorted({min(ncpu, 32), min(ncpu, 16), min(ncpu, 64), ncpu}):
         torch.set_num_threads(nt)
-        once()
         t = once()
         if best is None or t < best[0]:
             best = (t, nt)
+        if t > 3 * best[0]:
+            break  # more threads are clearly worse on this host
     cores = best[1]
     torch.set_num_threads(cores)
     times = []
