@@ -146,6 +146,34 @@ def cpu_reference_sample(repeats, warmup=0):
     return value, t, cores
 
 
+def gpu_eager_reference_sample(dev, repeats=3):
+    """The reference's own eager fp32 PyTorch path (oracle port, ATen kernels, TF32 off) on the SAME GPU, bounded sample
+    B=1,H=2,K=1,F=243 with flip TTA — the GPU-to-GPU comparison the reference itself would give on this box."""
+    import torch
+    from d3dp_b200.synthetic import (H36M_JOINTS_LEFT as JL, H36M_JOINTS_RIGHT as JR, synthetic_inputs,
+                                     synthetic_pose_estimator_state)
+    from oracle import d3dp_oracle as orc
+    torch.backends.cuda.matmul.allow_tf32 = False
+    H = 2
+    sd = {k: v.to(dev) for k, v in synthetic_pose_estimator_state(F_FRAMES, seed=0).items()}
+    x2d, x2d_flip, n0, ns = [t.to(dev) for t in synthetic_inputs(1, H, 1, F_FRAMES)]
+    bufs = {k: v.to(dev) for k, v in orc.schedule_buffers(1000).items()}
+
+    def once():
+        with torch.no_grad():
+            return orc.ddim_sample(sd, x2d, x2d_flip, H, 1, n0, ns, JL, JR, buffers=bufs)
+    once()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(repeats):
+        once()
+    e.record()
+    torch.cuda.synchronize()
+    t = s.elapsed_time(e) / repeats * 1e-3
+    return F_FRAMES * H / (t * H_PER_GPU * K_STEPS), t
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
@@ -353,6 +381,14 @@ def run_ours(args, rank, world, local_rank):
     }
     if cpu_line:
         line["cpu_baseline"] = cpu_line
+        try:
+            v, t_s = gpu_eager_reference_sample(dev)
+            line["gpu_eager_baseline"] = {
+                "value": v, "unit": "poses/s", "kind": "port", "speedup": value / v,
+                "sample": f"oracle port of the reference's eager fp32 PyTorch path on this GPU (ATen, TF32 off), "
+                          f"B=1 H=2 K=1 F=243 flip, {t_s * 1e3:.0f} ms, scaled by B*H*K linearity"}
+        except Exception as ex:  # never let the extra baseline break the bench line
+            line["gpu_eager_baseline"] = {"error": str(ex)[:200]}
     print(json.dumps(line), flush=True)
 
 

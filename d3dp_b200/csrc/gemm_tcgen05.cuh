@@ -192,37 +192,40 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll 1
       for (int sl = 0; sl < COLS_PER_THREAD / 64; ++sl) {
         uint8_t* buf = gbuf + (sl & 1) * 16384;
+        // both 32-column chunks of the slab are read from TMEM before any math (one exposed TMEM latency per slab,
+        // overlapped with the wait for the staging buffer)
+        uint32_t v0[32], v1[32];
+        tmem_ld32(taddr + sl * 64, v0);
+        tmem_ld32(taddr + sl * 64 + 32, v1);
         if (leader) tma_store_wait_read<1>();
         named_bar_sync(2 + split, 128);
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = sl * 2 + cc;
-          uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
-          uint32_t o[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float2 bb = *reinterpret_cast<const float2*>(sprm + n0 + c * 32 + 2 * i);
-            float a = __uint_as_float(v[2 * i]) + bb.x;
-            float b = __uint_as_float(v[2 * i + 1]) + bb.y;
-            if constexpr (EPI == EPI_BIAS_GELU_F16) {
-              a = gelu_erf(a);
-              b = gelu_erf(b);
-            }
-            o[i] = pack_half2(a, b);
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int piece = cc * 4 + i;
-            *reinterpret_cast<uint4*>(buf + r * 128 + ((piece ^ (r & 7)) << 4)) =
-                make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-          }
-        }
-        if (sl == COLS_PER_THREAD / 64 - 1) {
+        tmem_ld_wait();
+        if (sl == COLS_PER_THREAD / 64 - 1) {  // all accumulator columns of this thread are in registers: free the stage
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(tempty_leader0 + as * 8);  // the leader's MMA thread owns the pair's TMEM
+        }
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = sl * 2 + cc;
+          const uint32_t(&v)[32] = cc == 0 ? v0 : v1;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {  // 8 columns -> one 16-byte piece of the 128-byte slab row
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 bb = *reinterpret_cast<const float2*>(sprm + n0 + c * 32 + 8 * i + 2 * q);
+              float a = __uint_as_float(v[8 * i + 2 * q]) + bb.x;
+              float b = __uint_as_float(v[8 * i + 2 * q + 1]) + bb.y;
+              if constexpr (EPI == EPI_BIAS_GELU_F16) {
+                a = gelu_erf(a);
+                b = gelu_erf(b);
+              }
+              o[q] = pack_half2(a, b);
+            }
+            const int piece = cc * 4 + i;
+            *reinterpret_cast<uint4*>(buf + r * 128 + ((piece ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
         }
         fence_proxy_async_smem();
         named_bar_sync(2 + split, 128);

@@ -1,8 +1,9 @@
 """CPU oracle for the D3DP diffusion-sampling hot path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
 A plain float32 (float64 where the reference is float64) restatement, on the CPU, of what the reference computes on
-this path.  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline / `--impl reference` legs may
-import it; nothing under `d3dp_b200/` does.
+this path.  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s baseline legs (CPU baseline, `--impl
+reference`, and the same-GPU eager-PyTorch baseline, which runs these same functions on CUDA tensors) may import it;
+nothing under `d3dp_b200/` does.
 
 The reference's arithmetic for this path *is* PyTorch ATen (addmm / bmm / softmax / layer_norm / gelu; SURVEY §8c:
 torch unpinned in the reference, 2.11.0 here), so the restatement uses the same ATen ops on CPU tensors, but in one
@@ -85,7 +86,7 @@ def time_embedding(sd, t):
     """SinusoidalPositionEmbeddings + time_mlp (common/mixste.py:127-139,179-184). t: int64 [B] -> [B,512]."""
     half = 256
     e = math.log(10000) / (half - 1)
-    e = torch.exp(torch.arange(half) * -e)
+    e = torch.exp(torch.arange(half, device=t.device) * -e)
     e = t[:, None] * e[None, :]
     e = torch.cat((e.sin(), e.cos()), dim=-1)
     e = Fn.gelu(Fn.linear(e, sd["time_mlp.1.weight"], sd["time_mlp.1.bias"]))
@@ -143,7 +144,7 @@ def ddim_sample(sd, x2d, x2d_flip, H, K, noise_init, noise_steps, joints_left, j
     img = noise_init.clone()
     preds = []
     for k, (t, t_next) in enumerate(zip(times[:-1], times[1:])):
-        tc = torch.full((B,), t, dtype=torch.long)
+        tc = torch.full((B,), t, dtype=torch.long, device=x2d.device)
         x_t = torch.clamp(img, min=-1.1 * scale, max=1.1 * scale) / scale                   # :148-149
         pred = denoiser(sd, x2d, x_t, tc, depth)
         if x2d_flip is not None:
