@@ -65,22 +65,35 @@ class MixSTE2(nn.Module):
         self._engines = {}  # device index -> (Engine, weights fingerprint); shared by DataParallel replicas
 
     # ------------------------------------------------------------------ engine management
-    def _fingerprint(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+    def _named_weights(self):
+        """{reference state_dict key: tensor} for this module tree.  Also works inside nn.DataParallel replicas, whose
+        parameters are plain attributes recorded in `_former_parameters` (state_dict() / parameters() are empty there)."""
+        out = {}
+        for mod_name, mod in self.named_modules():
+            params = dict(mod._parameters)
+            params.update(getattr(mod, "_former_parameters", {}))
+            for k, v in params.items():
+                if v is not None:
+                    out[(mod_name + "." if mod_name else "") + k] = v
+        return out
+
+    def _fingerprint(self, weights):
+        return tuple((p.data_ptr(), p._version) for p in weights.values())
 
     def engine(self):
         """The per-device Engine with this module's current weights uploaded (re-packed when any parameter changed)."""
-        p0 = self.Spatial_pos_embed
+        weights = self._named_weights()
+        p0 = weights["Spatial_pos_embed"]
         if p0.device.type != "cuda":
             raise RuntimeError("d3dp_b200.MixSTE2 runs on CUDA (sm_100a) only: move the module with .cuda() first")
         idx = p0.device.index if p0.device.index is not None else torch.cuda.current_device()
-        fp = self._fingerprint()
+        fp = self._fingerprint(weights)
         ent = self._engines.get(idx)
         if ent is None or ent[1] != fp:
             with torch.cuda.device(idx):
                 eng = ent[0] if ent is not None else Engine(
                     self.num_frame, self._joints_left, self._joints_right, depth=self.block_depth, scale=self._scale)
-                eng.load_pose_estimator_state({k: v for k, v in self.state_dict().items()})
+                eng.load_pose_estimator_state(weights)
             self._engines[idx] = (eng, fp)
             ent = self._engines[idx]
         return ent[0]
