@@ -69,7 +69,7 @@ attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParam
       const uint32_t bytes = 3u * p.rows * 128u;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int seq = item >> 3, head = item & 7;
-        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_wait_backoff(&empty_bar[s], ph ^ 1);
         uint8_t* st = smem + s * ATT_STAGE_BYTES;
         mbar_expect_tx(&full_bar[s], bytes);
         const int row0 = seq * p.F;
@@ -307,7 +307,7 @@ attn_temporal_long_kernel(const __grid_constant__ CUtensorMap tmQKV /* box {64, 
       const uint32_t bytes = 3u * p.rows * 128u;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int seq = item >> 3, head = item & 7;
-        mbar_wait(empty_bar, ph ^ 1);
+        mbar_wait_backoff(empty_bar, ph ^ 1);
         mbar_expect_tx(full_bar, bytes);
         const int row0 = seq * p.F;
         for (int t3 = 0; t3 < 3; ++t3)

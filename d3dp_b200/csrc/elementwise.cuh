@@ -114,6 +114,17 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int BH = p.B * p.H;
   const long long T = static_cast<long long>(p.n_streams) * kJ * p.F;
+  // lane owns channels c = i*32 + lane: its slice of W_e, b_e and the norm1 affine stays in registers for all tokens
+  float we[16][5], be[16], lg[16], lb[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = i * 32 + lane;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) we[i][k] = p.w_e[c * 5 + k];
+    be[i] = p.b_e[c];
+    lg[i] = p.ln_g[c];
+    lb[i] = p.ln_b[c];
+  }
   for (long long row = warp; row < T; row += nwarps) {
     const int f = static_cast<int>(row % p.F);
     const long long sj = row / p.F;
@@ -137,16 +148,16 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
       }
       if (flip) in[2] = -in[2];
     }
+    const float* sp = p.spos + j * kC + lane;
+    const float* ta = p.tau + static_cast<size_t>(b) * kC + lane;
     float v[16];
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const int c = i * 32 + lane;
-      const float* w = p.w_e + c * 5;
-      float acc = p.b_e[c];
+      float acc = be[i];
 #pragma unroll
-      for (int k = 0; k < 5; ++k) acc += w[k] * in[k];
-      acc += p.spos[j * kC + c] + p.tau[static_cast<size_t>(b) * kC + c];
+      for (int k = 0; k < 5; ++k) acc += we[i][k] * in[k];
+      acc += sp[i * 32] + ta[i * 32];
       v[i] = acc;
       sum += acc;
     }
@@ -159,13 +170,12 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
 #pragma unroll
     for (int d = 16; d; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
     const float rstd = rsqrtf(sq * (1.0f / kC) + p.ln_eps);
-    float* xr = p.x + row * kC;
-    __half* ar = p.a16 + row * kC;
+    float* xr = p.x + row * kC + lane;
+    __half* ar = p.a16 + row * kC + lane;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const int c = i * 32 + lane;
-      xr[c] = v[i];
-      ar[c] = __float2half_rn((v[i] - mean) * rstd * p.ln_g[c] + p.ln_b[c]);
+      xr[i * 32] = v[i];
+      ar[i * 32] = __float2half_rn((v[i] - mean) * rstd * lg[i] + lb[i]);
     }
   }
 }

@@ -113,7 +113,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t ph = 0;
       for (int tile = cluster_id; tile < tiles_m; tile += num_clusters) {
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_wait_backoff(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
           // the pair shares the A tile: each CTA fetches 64 of its 128 rows and multicasts them to both
@@ -159,7 +159,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int bi = g * RING + slot;
-            mbar_wait(&rempty_bar[bi], ph ^ 1);
+            mbar_wait_backoff(&rempty_bar[bi], ph ^ 1);
             mbar_expect_tx(&rfull_bar[bi], L::SLOT_BYTES);
             tma_load_2d(smem + L::RING_OFFSET + bi * L::SLOT_BYTES, &tmX, &rfull_bar[bi],
                         ncol0 + g * 128 + c * 32, tile * 128);

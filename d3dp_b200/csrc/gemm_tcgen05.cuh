@@ -135,7 +135,7 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
         const int m_blk = (ct / tiles_n) * 2 + rank, n_blk = ct % tiles_n;
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_wait_backoff(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
           const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[s]), 0);
           if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * L::STAGE_BYTES);

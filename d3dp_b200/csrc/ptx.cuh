@@ -56,6 +56,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Same with a short sleep between polls: for the producer threads, whose waits (a free stage) are long and not
+// latency critical — a third of all executed instructions in the GEMM kernels were their spin loops, taking issue
+// slots from the epilogue warps on the same scheduler and power from the clocks.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+}
 
 // ---------------------------------------------------------------- clusters / distributed shared memory
 __device__ __forceinline__ uint32_t cluster_ctarank() {
