@@ -440,7 +440,7 @@ int d3dp_create(const d3dp_config* cfg, d3dp_handle** out) {
   if (!cfg || !out) return D3DP_E_INVALID;
   *out = nullptr;
   if (cfg->joints != 17 || cfg->channels != 512 || cfg->heads != 8 || cfg->mlp_hidden != 1024 ||
-      cfg->depth < 1 || cfg->depth > 8 || cfg->frames < 1 || cfg->frames > 384 || cfg->num_timesteps < 1)
+      !(cfg->output_scale > 0.f) || cfg->depth < 1 || cfg->depth > 8 || cfg->frames < 1 || cfg->frames > 384 || cfg->num_timesteps < 1)
     return D3DP_E_INVALID;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return D3DP_E_CUDA;
@@ -642,6 +642,7 @@ int d3dp_ddim_sample(d3dp_handle* h, const float* x2d, const float* x2d_flip, co
     dp.B = B; dp.H = H; dp.K = K; dp.F = F; dp.k = k;
     dp.flip = flip; dp.last = t_next < 0 ? 1 : 0;
     dp.scale = scale;
+    dp.out_scale = h->cfg.output_scale;
     dp.sqrt_recip_ac = h->sqrt_recip[t];
     dp.sqrt_recipm1_ac = h->sqrt_recipm1[t];
     if (t_next >= 0) {
@@ -673,19 +674,27 @@ int d3dp_q_sample(d3dp_handle* h, const float* x0, const float* noise, const int
   return D3DP_OK;
 }
 
-int d3dp_jpma(d3dp_handle* h, const float* preds, const float* traj, const float* cam, const float* x2d,
-              float* jagg_pose, int32_t* jagg_idx, float* pagg_pose, float* e2d_min, int32_t B, int32_t K, int32_t H,
-              int32_t root_joint, int32_t linear, void* stream) {
+int d3dp_jpma_gt(d3dp_handle* h, const float* preds, const float* traj, const float* cam, const float* x2d,
+                 const float* gt, float* jagg_pose, int32_t* jagg_idx, float* pagg_pose, float* e2d_min, float* e3d,
+                 float* jbest_pose, int32_t B, int32_t K, int32_t H, int32_t root_joint, int32_t linear, void* stream) {
   if (!h || !preds || !traj || !cam || !x2d || !jagg_pose || !jagg_idx || !pagg_pose || B < 1 || K < 1 || H < 1)
     return fail(h, D3DP_E_INVALID, "jpma: bad argument");
   JpmaParams p;
   p.pred = preds; p.traj = traj; p.cam = cam; p.x2d = x2d;
   p.jagg_pose = jagg_pose; p.jagg_idx = jagg_idx; p.pagg_pose = pagg_pose; p.e2d_min = e2d_min;
+  p.gt = gt; p.e3d = gt ? e3d : nullptr; p.jbest_pose = gt ? jbest_pose : nullptr;
   p.B = B; p.K = K; p.H = H; p.F = h->cfg.frames; p.root = root_joint; p.linear = linear;
   const long long n = static_cast<long long>(B) * K * p.F * kJ;
   jpma_kernel<<<grid_for(n, h->num_sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   CK(cudaGetLastError());
   return D3DP_OK;
+}
+
+int d3dp_jpma(d3dp_handle* h, const float* preds, const float* traj, const float* cam, const float* x2d,
+              float* jagg_pose, int32_t* jagg_idx, float* pagg_pose, float* e2d_min, int32_t B, int32_t K, int32_t H,
+              int32_t root_joint, int32_t linear, void* stream) {
+  return d3dp_jpma_gt(h, preds, traj, cam, x2d, nullptr, jagg_pose, jagg_idx, pagg_pose, e2d_min, nullptr, nullptr, B, K,
+                      H, root_joint, linear, stream);
 }
 
 int d3dp_philox_normal(d3dp_handle* h, float* out, int32_t B, int32_t H, int64_t per_bh, uint64_t seed,

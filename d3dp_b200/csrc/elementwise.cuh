@@ -251,6 +251,7 @@ struct DdimParams {
   int flip;             // 1: TTA streams present
   int last;             // 1: img = x0
   float scale;
+  float out_scale;      // preds are stored as x0 * out_scale (1000 for the 3DHP / mm variant)
   double sqrt_recip_ac, sqrt_recipm1_ac;
   float sqrt_ac_next, c, sigma;
   unsigned long long seed;
@@ -278,7 +279,8 @@ __global__ void __launch_bounds__(256) ddim_step_kernel(const DdimParams p) {
     float x0 = __fmul_rn(pred, p.scale);
     x0 = fminf(fmaxf(x0, -1.1f * p.scale), 1.1f * p.scale);
     const int b = static_cast<int>(bh / p.H), h = static_cast<int>(bh % p.H);
-    p.preds[(((static_cast<long long>(b) * p.K + p.k) * p.H + h) * per_bh) + (i - bh * per_bh)] = x0;
+    p.preds[(((static_cast<long long>(b) * p.K + p.k) * p.H + h) * per_bh) + (i - bh * per_bh)] =
+        p.out_scale == 1.0f ? x0 : __fmul_rn(x0, p.out_scale);
     if (p.last) {
       p.img[i] = x0;
     } else {
@@ -348,6 +350,9 @@ struct JpmaParams {
   int* jagg_idx;       // [B,K,F,17]
   float* pagg_pose;    // [B,K,F,17,3]
   float* e2d_min;      // [B,K,F,17] or null
+  const float* gt;     // [B,F,17,3] or null (evaluation)
+  float* e3d;          // [B,K,H,F,17] or null: ||pred - gt|| per hypothesis
+  float* jbest_pose;   // [B,K,F,17,3] or null: argmin_h e3d
   int B, K, H, F, root;
   int linear;          // 1: project_to_2d_linear (focal + principal point only)
 };
@@ -367,6 +372,11 @@ __global__ void __launch_bounds__(256) jpma_kernel(const JpmaParams p) {
     float best = INFINITY;
     int best_h = 0;
     float bx = 0.f, by = 0.f, bz = 0.f;
+    float best3 = INFINITY, jx = 0.f, jy = 0.f, jz = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
+    if (p.gt) {
+      const float* gp = p.gt + ((static_cast<size_t>(b) * p.F + f) * kJ + j) * 3;
+      gx = gp[0]; gy = gp[1]; gz = gp[2];
+    }
     float sx = 0.f, sy = 0.f, sz = 0.f;
     for (int h = 0; h < p.H; ++h) {
       const float* q =
@@ -397,6 +407,12 @@ __global__ void __launch_bounds__(256) jpma_kernel(const JpmaParams p) {
       }
       const float du = __fsub_rn(pu, u), dv = __fsub_rn(pv, v);
       const float e = __fsqrt_rn(__fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)));
+      if (p.gt) {
+        const float ax = __fsub_rn(px, gx), ay = __fsub_rn(py, gy), az = __fsub_rn(pz, gz);
+        const float e3 = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az)));
+        if (p.e3d) p.e3d[(((static_cast<size_t>(b) * p.K + k) * p.H + h) * p.F + f) * kJ + j] = e3;
+        if (e3 < best3) { best3 = e3; jx = px; jy = py; jz = pz; }
+      }
       if (e < best) {  // strict: first index wins ties, like torch.min
         best = e;
         best_h = h;
@@ -410,6 +426,10 @@ __global__ void __launch_bounds__(256) jpma_kernel(const JpmaParams p) {
     float* po = p.pagg_pose + i * 3;
     po[0] = sx * invH; po[1] = sy * invH; po[2] = sz * invH;
     if (p.e2d_min) p.e2d_min[i] = best;
+    if (p.gt && p.jbest_pose) {
+      float* bo = p.jbest_pose + i * 3;
+      bo[0] = jx; bo[1] = jy; bo[2] = jz;
+    }
   }
 }
 

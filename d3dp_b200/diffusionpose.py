@@ -32,6 +32,8 @@ def cosine_beta_schedule(timesteps, s=0.008):
 
 
 class D3DP(nn.Module):
+    OUTPUT_SCALE = 1.0  # common/diffusionpose_3dhp.py multiplies every returned pose by 1000 (see diffusionpose_3dhp)
+
     def __init__(self, args, joints_left, joints_right, is_train=True, num_proposals=1, sampling_timesteps=1):
         super().__init__()
         self.frames = args.number_of_frames
@@ -72,7 +74,8 @@ class D3DP(nn.Module):
         self.pose_estimator = MixSTE2(
             num_frame=self.frames, num_joints=17, in_chans=2, embed_dim_ratio=args.cs, depth=args.dep, num_heads=8,
             mlp_ratio=2., qkv_bias=True, qk_scale=None, drop_path_rate=0.1 if is_train else 0, is_train=is_train,
-            joints_left=self.joints_left, joints_right=self.joints_right, scale=args.scale)
+            joints_left=self.joints_left, joints_right=self.joints_right, scale=args.scale,
+            output_scale=self.OUTPUT_SCALE)
         self._sched_fp = {}
 
     # ------------------------------------------------------------------ engine
@@ -150,5 +153,6 @@ class D3DP(nn.Module):
             if self.flip:
                 return self.ddim_sample_flip(input_2d, input_3d, input_2d_flip=input_2d_flip)
             return self.ddim_sample(input_2d, input_3d)
-        x_poses, noises, t = self.prepare_targets(input_3d)
-        return self.pose_estimator(input_2d, x_poses.float(), t.squeeze(-1))
+        x_poses, noises, t = self.prepare_targets(input_3d / self.OUTPUT_SCALE if self.OUTPUT_SCALE != 1.0 else input_3d)
+        pred = self.pose_estimator(input_2d, x_poses.float(), t.squeeze(-1))
+        return pred * self.OUTPUT_SCALE if self.OUTPUT_SCALE != 1.0 else pred

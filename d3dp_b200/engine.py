@@ -25,7 +25,7 @@ def _stream():
 
 class Engine:
     def __init__(self, frames, joints_left=H36M_JOINTS_LEFT, joints_right=H36M_JOINTS_RIGHT, depth=8, channels=512,
-                 scale=1.0, num_timesteps=1000, device=None):
+                 scale=1.0, num_timesteps=1000, device=None, output_scale=1.0):
         if not torch.cuda.is_available():
             raise D3dpError("d3dp_b200 needs a CUDA device (sm_100a); there is no CPU path")
         self.lib = _lib.load()
@@ -36,6 +36,7 @@ class Engine:
         cfg.heads, cfg.mlp_hidden, cfg.num_timesteps, cfg.scale = 8, 2 * channels, num_timesteps, float(scale)
         for j, s in enumerate(flip_permutation(joints_left, joints_right)):
             cfg.flip_perm[j] = s
+        cfg.output_scale = float(output_scale)
         self.handle = C.c_void_p()
         with torch.cuda.device(self.device):
             rc = self.lib.d3dp_create(C.byref(cfg), C.byref(self.handle))
@@ -145,6 +146,22 @@ class Engine:
                                                   ptr(idx), ptr(pagg), ptr(e2d), B, K, H, int(root_joint), int(linear),
                                                   _stream()), "d3dp_jpma")
         return (jagg, idx, pagg, e2d) if return_e2d else (jagg, idx, pagg)
+
+    def jpma_gt(self, preds, traj, cam, x2d, gt, root_joint=0, linear=False):
+        """JPMA plus the ground-truth-dependent outputs (per-hypothesis 3-D errors, J-Best pose)."""
+        preds, traj, cam, x2d, gt = (self._f32(t) for t in (preds, traj, cam, x2d, gt))
+        B, K, H = preds.shape[0], preds.shape[1], preds.shape[2]
+        traj = traj.reshape(B, self.frames, 3)
+        if cam.dim() == 1:
+            cam = cam[None].expand(B, 9).contiguous()
+        new = lambda *shape, dt=torch.float32: torch.empty(*shape, dtype=dt, device=self.device)  # noqa: E731
+        jagg, pagg, jbest = (new(B, K, self.frames, 17, 3) for _ in range(3))
+        idx, e2d, e3d = new(B, K, self.frames, 17, dt=torch.int32), new(B, K, self.frames, 17), new(B, K, H, self.frames, 17)
+        with torch.cuda.device(self.device):
+            check(self.handle, self.lib.d3dp_jpma_gt(
+                self.handle, ptr(preds), ptr(traj), ptr(cam), ptr(x2d), ptr(gt), ptr(jagg), ptr(idx), ptr(pagg),
+                ptr(e2d), ptr(e3d), ptr(jbest), B, K, H, int(root_joint), int(linear), _stream()), "d3dp_jpma_gt")
+        return {"jagg_pose": jagg, "jagg_idx": idx, "pagg_pose": pagg, "e2d_min": e2d, "e3d": e3d, "jbest_pose": jbest}
 
     def philox_normal(self, B, H, per_bh, seed, h_offset=0, H_total=None, draw=0):
         out = torch.empty(B, H, per_bh, dtype=torch.float32, device=self.device)

@@ -39,7 +39,8 @@ class _Block(nn.Module):  # parameter holder for common/mixste.py:84-111
 class MixSTE2(nn.Module):
     def __init__(self, num_frame=9, num_joints=17, in_chans=2, embed_dim_ratio=32, depth=4, num_heads=8, mlp_ratio=2.,
                  qkv_bias=True, qk_scale=None, drop_rate=0., attn_drop_rate=0., drop_path_rate=0.2, norm_layer=None,
-                 is_train=True, joints_left=H36M_JOINTS_LEFT, joints_right=H36M_JOINTS_RIGHT, scale=1.0):
+                 is_train=True, joints_left=H36M_JOINTS_LEFT, joints_right=H36M_JOINTS_RIGHT, scale=1.0,
+                 output_scale=1.0):
         super().__init__()
         if (num_joints, in_chans, embed_dim_ratio, num_heads, float(mlp_ratio), bool(qkv_bias), qk_scale) != \
                 (17, 2, 512, 8, 2.0, True, None):
@@ -52,6 +53,7 @@ class MixSTE2(nn.Module):
         self.is_train = is_train
         self.num_frame, self.block_depth = num_frame, depth
         self._joints_left, self._joints_right, self._scale = list(joints_left), list(joints_right), float(scale)
+        self._output_scale = float(output_scale)  # sampler outputs are stored as x0 * output_scale (3DHP: 1000)
         self.Spatial_patch_to_embedding = nn.Linear(in_chans + 3, C)
         self.Spatial_pos_embed = nn.Parameter(torch.zeros(1, num_joints, C))
         self.Temporal_pos_embed = nn.Parameter(torch.zeros(1, num_frame, C))
@@ -92,7 +94,8 @@ class MixSTE2(nn.Module):
         if ent is None or ent[1] != fp:
             with torch.cuda.device(idx):
                 eng = ent[0] if ent is not None else Engine(
-                    self.num_frame, self._joints_left, self._joints_right, depth=self.block_depth, scale=self._scale)
+                    self.num_frame, self._joints_left, self._joints_right, depth=self.block_depth, scale=self._scale,
+                    output_scale=self._output_scale)
                 eng.load_pose_estimator_state(weights)
             self._engines[idx] = (eng, fp)
             ent = self._engines[idx]

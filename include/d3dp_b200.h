@@ -47,6 +47,7 @@ typedef struct d3dp_config {
   int32_t num_timesteps;  /* args.timestep, 1000                                                  */
   float scale;            /* args.scale                                                           */
   int32_t flip_perm[17];  /* joint permutation of the flip TTA: perm[j] = source joint of j       */
+  float output_scale;     /* 1.0; 1000.0 reproduces common/diffusionpose_3dhp.py:212,256 (mm units) */
 } d3dp_config;
 
 /* D3DP.__init__ / MixSTE2.__init__ (common/diffusionpose.py:60, common/mixste.py:142): allocate a handle.
@@ -110,6 +111,15 @@ int d3dp_q_sample(d3dp_handle* h, const float* x0, const float* noise, const int
 int d3dp_jpma(d3dp_handle* h, const float* preds, const float* traj, const float* cam, const float* x2d,
               float* jagg_pose, int32_t* jagg_idx, float* pagg_pose, float* e2d_min, int32_t B, int32_t K, int32_t H,
               int32_t root_joint, int32_t linear, void* stream);
+
+/* JPMA with ground truth (evaluation only; main.py:715-718 metrics and main_3dhp.py:785-799 pose export):
+ * everything d3dp_jpma produces plus, against gt[B,F,17,3] (root joint zeroed by the caller like main.py:683),
+ *   e3d        [B,K,H,F,17]  per-hypothesis 3-D error ||pred - gt|| (input of J-Best / P-Best),
+ *   jbest_pose [B,K,F,17,3]  per-joint oracle-best hypothesis (argmin_h e3d, main_3dhp.py:797-799),
+ * either may be NULL. */
+int d3dp_jpma_gt(d3dp_handle* h, const float* preds, const float* traj, const float* cam, const float* x2d,
+                 const float* gt, float* jagg_pose, int32_t* jagg_idx, float* pagg_pose, float* e2d_min, float* e3d,
+                 float* jbest_pose, int32_t B, int32_t K, int32_t H, int32_t root_joint, int32_t linear, void* stream);
 
 /* Standard-normal Philox fill used for the sampler's noise, exposed so callers/tests can reproduce it:
  * out[B,H,per_bh] for draw index `draw`, hypotheses h_offset..h_offset+H-1 of H_total. */

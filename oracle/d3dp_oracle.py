@@ -220,6 +220,41 @@ def jpma(preds, traj, cam, x2d, root_joint=0, linear=False):
     return jagg, idx.squeeze(2), pagg, mn.values.squeeze(2)
 
 
+def jpma_errors(preds, gt, traj, cam, x2d, root_joint=0, linear=False):
+    """The four per-step errors main.py:715-718 logs — J-Best (common/loss.py:22-40 mpjpe_diffusion_all_min), P-Best
+    (:78-94 mpjpe_diffusion), P-Agg (:42-52 mean_pos branch), J-Agg (:54-76 mpjpe_diffusion_reproj) — as [K] tensors.
+    preds [B,K,H,F,17,3] (root joint zeroed here like main.py:700), gt [B,F,17,3] with the root joint zeroed."""
+    B, K, H, F = preds.shape[:4]
+    P = preds.clone()
+    P[:, :, :, :, root_joint] = 0
+    e3d = torch.norm(P - gt.reshape(B, 1, 1, F, J, 3), dim=-1)                                   # [B,K,H,F,17]
+    j_best = e3d.permute(1, 2, 0, 3, 4).min(dim=1).values.reshape(K, -1).mean(-1)
+    p_best = e3d.permute(1, 2, 0, 3, 4).reshape(K, H, -1).mean(-1).min(dim=1).values
+    jagg, idx, pagg, _ = jpma(preds, traj, cam, x2d, root_joint, linear)
+    p_agg = torch.norm(pagg - gt[:, None], dim=-1).permute(1, 0, 2, 3).reshape(K, -1).mean(-1)
+    sel = torch.gather(e3d, 2, idx.unsqueeze(2))                                                # error of the selected h
+    j_agg = sel.permute(1, 2, 0, 3, 4).reshape(K, -1).mean(-1)
+    jbest_idx = e3d.min(dim=2, keepdim=True).indices
+    jbest_pose = torch.gather(P, 2, jbest_idx.unsqueeze(-1).expand(B, K, 1, F, J, 3)).squeeze(2)
+    return {"J-Best": j_best, "P-Best": p_best, "P-Agg": p_agg, "J-Agg": j_agg, "e3d": e3d, "jbest_pose": jbest_pose}
+
+
+def eval_data_prepare(receptive_field, inputs_2d):
+    """main.py:267-299 for one sequence [N,17,C]: ceil(N/F) clips, the last one = the last F frames; replicate-pad
+    sequences shorter than F."""
+    F = receptive_field
+    x = inputs_2d
+    n = x.shape[0]
+    out_num = n // F + (1 if n % F else 0)
+    out = torch.empty(max(out_num, 1), F, x.shape[1], x.shape[2])
+    for i in range(out_num - 1):
+        out[i] = x[i * F:(i + 1) * F]
+    if n < F:
+        x = torch.cat([x, x[-1:].repeat(F - n, 1, 1)], dim=0)
+    out[-1] = x[-F:]
+    return out
+
+
 def mpjpe_distance(a, b):
     """Parity metric: mean / max over all joints of the per-joint L2 distance."""
     d = torch.norm(a.double() - b.double(), dim=-1)

@@ -65,6 +65,14 @@ def main():
     print("J-Agg per-step error ref", e_ref.tolist(), "oracle", e_mine.tolist())
     print("P-Agg per-step error ref", p_ref.tolist(), "oracle", p_mine.tolist())
     ok &= torch.allclose(e_ref, e_mine, atol=1e-6) and torch.allclose(p_ref, p_mine, atol=1e-6)
+    # all four logged errors (main.py:715-718) through the oracle's jpma_errors
+    from common.loss import mpjpe_diffusion
+    errs = orc.jpma_errors(ref, gt, traj, cam, x2d)
+    refs = {"J-Best": mpjpe_diffusion_all_min(pred, gt), "P-Best": mpjpe_diffusion(pred, gt), "P-Agg": p_ref, "J-Agg": e_ref}
+    for k, v in refs.items():
+        same = torch.allclose(v, errs[k], atol=1e-6)
+        print(f"{k:7s} ref {v.tolist()} oracle {errs[k].tolist()} {'ok' if same else 'MISMATCH'}")
+        ok &= same
     print("ORACLE PINNED" if ok else "ORACLE MISMATCH")
     return 0 if ok else 1
 

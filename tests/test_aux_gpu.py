@@ -150,3 +150,41 @@ def test_dataparallel_two_gpus_matches_single_gpu():
     # same clips through the same weights on each device: the per-clip statistics must agree with the 1-GPU run's
     # (noise differs: DataParallel replicas draw from their own device generators, exactly like the reference)
     assert abs(out.abs().mean().item() - ref.abs().mean().item()) < 0.05
+
+
+def test_jpma_metrics_match_oracle():
+    """J-Best / P-Best / P-Agg / J-Agg errors (main.py:715-718) from the fused kernel vs the oracle restatement of
+    common/loss.py; J-Best pose gather (main_3dhp.py:797-799)."""
+    from d3dp_b200.metrics import jpma_metrics
+    from d3dp_b200.synthetic import synthetic_camera
+    g = torch.Generator().manual_seed(11)
+    B, K, H, F = 2, 3, 20, 27
+    gt = 0.4 * torch.randn(B, F, 17, 3, generator=g)
+    gt[:, :, 0] = 0
+    preds = gt[:, None, None] + 0.05 * torch.randn(B, K, H, F, 17, 3, generator=g)
+    x2d = 0.3 * torch.randn(B, F, 17, 2, generator=g)
+    traj, cam = synthetic_camera(B, F)
+    ref = orc.jpma_errors(preds, gt, traj, cam, x2d)
+    out = jpma_metrics(_engine(F), preds, gt, traj, cam, x2d)
+    for k in ("J-Best", "P-Best", "P-Agg", "J-Agg"):
+        assert torch.allclose(out[k].cpu(), ref[k], atol=2e-6), k
+    assert torch.allclose(out["e3d"].cpu(), ref["e3d"], atol=1e-6)
+    assert torch.equal(out["jbest_pose"].cpu()[..., 1:, :], ref["jbest_pose"][..., 1:, :])
+    assert (out["J-Best"] <= out["J-Agg"] + 1e-6).all() and (out["J-Best"] <= out["P-Best"] + 1e-6).all()
+
+
+def test_3dhp_variant_outputs_millimetres():
+    """common/diffusionpose_3dhp.py: identical sampler, outputs x1000 (applied inside the DDIM kernel)."""
+    from d3dp_b200.diffusionpose_3dhp import D3DP as D3DP3
+    from tests.util import make_args
+    case = load_golden("f27_flip")
+    sd, x2d, x2d_flip, n0, ns = case_inputs(case)
+    m = D3DP3(make_args(27), JL, JR, is_train=False, num_proposals=case["H"], sampling_timesteps=case["K"])
+    m.pose_estimator.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    out = m.ddim_sample_flip(x2d.cuda(), None, input_2d_flip=x2d_flip.cuda(), noise_init=n0, noise_steps=ns)
+    base = build_model(27, case["H"], case["K"], sd).ddim_sample_flip(
+        x2d.cuda(), None, input_2d_flip=x2d_flip.cuda(), noise_init=n0, noise_steps=ns)
+    assert torch.equal(out, base * 1000)  # same chain, one extra float32 multiply per stored value
+    mean, mx = mpjpe_distance(out / 1000, case["preds"])
+    assert mean < 1e-3

@@ -110,3 +110,47 @@ def test_shard_range_partitions_hypotheses():
             assert parts[0][0] == 0 and sum(n for _, n in parts) == H
             assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(W - 1))
             assert max(n for _, n in parts) - min(n for _, n in parts) <= 1
+
+
+def test_clip_pipeline_matches_reference_semantics():
+    """d3dp_b200.clips.eval_data_prepare == the oracle restatement of main.py:267-299 (and the reference itself where
+    its tree is present), for sequence lengths below, equal to, and above multiples of F."""
+    from d3dp_b200.clips import batches, eval_data_prepare, flip_inputs, stitch_clips
+    from d3dp_b200.synthetic import H36M_JOINTS_LEFT as JL, H36M_JOINTS_RIGHT as JR, flip_2d
+    from oracle import d3dp_oracle as orc
+    from oracle import ref_harness as rh
+    F = 27
+    ref_fn = None
+    if rh.available():
+        import importlib.util
+        import sys as _sys
+        rh.import_reference()
+        # main.py is a script; load only its eval_data_prepare by exec'ing the function source
+        src = open(os.path.join(rh.REF, "main.py")).read()
+        start = src.index("def eval_data_prepare(")
+        end = src.index("\n\n\n", start)
+        ns = {"torch": torch}
+        from einops import rearrange
+        ns["rearrange"] = rearrange
+        exec(src[start:end], ns)
+        ref_fn = ns["eval_data_prepare"]
+    for n in (5, 27, 28, 54, 100):
+        g = torch.Generator().manual_seed(n)
+        seq2d = torch.randn(1, n, 17, 2, generator=g)
+        seq3d = torch.randn(1, n, 17, 3, generator=g)
+        c2, c3 = eval_data_prepare(F, seq2d, seq3d)
+        assert torch.equal(c2, orc.eval_data_prepare(F, seq2d[0]))
+        assert torch.equal(c3, orc.eval_data_prepare(F, seq3d[0]))
+        if ref_fn is not None and n >= 2:
+            r2, r3 = ref_fn(F, seq2d, seq3d)
+            assert torch.equal(c2, r2) and torch.equal(c3, r3), n
+        assert torch.equal(stitch_clips(c2, n), seq2d[0])  # clips cover the sequence exactly once
+    assert torch.equal(flip_inputs(seq2d, JL, JR), flip_2d(seq2d))
+    assert [(s.start, s.stop) for s in batches(10, 4)] == [(0, 4), (4, 8), (8, 10)]
+
+
+def test_3dhp_variant_surface():
+    from d3dp_b200.diffusionpose_3dhp import D3DP as D3DP3
+    from tests.util import JL, JR, make_args
+    m = D3DP3(make_args(9, depth=1), JL, JR, is_train=False, num_proposals=1, sampling_timesteps=1)
+    assert m.OUTPUT_SCALE == 1000.0 and m.pose_estimator._output_scale == 1000.0 and len(m.state_dict()) == 12 + 40
