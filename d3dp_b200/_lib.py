@@ -12,7 +12,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libd3dp_b200.so")
 SYMBOLS = [
     "d3dp_create", "d3dp_destroy", "d3dp_last_error", "d3dp_set_weight", "d3dp_weights_missing",
     "d3dp_set_schedule", "d3dp_get_alphas_cumprod", "d3dp_time_list", "d3dp_workspace_bytes", "d3dp_denoise",
-    "d3dp_ddim_sample", "d3dp_q_sample", "d3dp_jpma", "d3dp_jpma_gt", "d3dp_philox_normal", "d3dp_test_gemm", "d3dp_test_attn",
+    "d3dp_ddim_sample", "d3dp_q_sample", "d3dp_jpma", "d3dp_jpma_gt", "d3dp_pmpjpe",
+    "d3dp_philox_normal", "d3dp_test_gemm", "d3dp_test_attn",
     "d3dp_version",
 ]
 
@@ -63,6 +64,7 @@ def load():
                               C.c_int32, C.c_int32, vp]
     lib.d3dp_jpma_gt.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, f32p, i32p, f32p, f32p, f32p, f32p, C.c_int32,
                                  C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+    lib.d3dp_pmpjpe.argtypes = [vp, f32p, f32p, f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
     lib.d3dp_philox_normal.argtypes = [vp, f32p, C.c_int32, C.c_int32, C.c_int64, C.c_uint64, C.c_int32, C.c_int32,
                                        C.c_uint32, vp]
     lib.d3dp_test_gemm.argtypes = [vp, C.c_int32, vp, vp, f32p, vp, f32p, f32p, f32p, C.c_float, f32p, f32p,

@@ -28,6 +28,20 @@ def eval_data_prepare(receptive_field, inputs_2d, inputs_3d=None):
     return cut(inputs_2d), cut(inputs_3d)
 
 
+def image_coordinates(x, w, h):
+    """Normalised screen coordinates -> pixels (common/camera.py:14-18), used on the 2-D target of the 3DHP J-Agg
+    selection (main_3dhp.py:829)."""
+    assert x.shape[-1] == 2
+    return (x + torch.tensor([1.0, h / w], dtype=x.dtype, device=x.device)) * (w / 2)
+
+
+def export_layout_3dhp(clip_poses, n_frames):
+    """MATLAB layout of the 3DHP pose export (main_3dhp.py:327-332 pose_post_process, :866-871): per-clip poses
+    [n_clips, K, F, 17, 3] of one sequence -> [3, 17, N, K] (the last clip supplies the last F frames)."""
+    seq = stitch_clips_last_wins(clip_poses, n_frames)     # [K, N, 17, 3]
+    return seq.permute(3, 2, 1, 0).contiguous()
+
+
 def flip_inputs(inputs_2d, kps_left, kps_right):
     """Test-time-augmentation input (main.py:646-648): negate x, swap left/right key points."""
     out = inputs_2d.clone()
@@ -52,3 +66,16 @@ def stitch_clips(clip_out, n_frames):
     tail = n_frames - (n_clips - 1) * F
     body.append(clip_out[-1][..., F - tail:, :, :])
     return torch.cat(body, dim=-3)
+
+
+def stitch_clips_last_wins(clip_out, n_frames):
+    """As stitch_clips, but the overlap is taken from the LAST clip, which is what the reference's export does
+    (main_3dhp.py:328-330 writes clips in order, then overwrites the last F frames)."""
+    F = clip_out.shape[-3]
+    n_clips = clip_out.shape[0]
+    if n_frames <= F:
+        return clip_out[0][..., :n_frames, :, :]
+    head = n_frames - F
+    full = [clip_out[i] for i in range(n_clips - 1)]
+    body = torch.cat(full, dim=-3)[..., :head, :, :]
+    return torch.cat([body, clip_out[-1]], dim=-3)

@@ -690,6 +690,18 @@ int d3dp_jpma_gt(d3dp_handle* h, const float* preds, const float* traj, const fl
   return D3DP_OK;
 }
 
+int d3dp_pmpjpe(d3dp_handle* h, const float* preds, const float* gt, float* perr, int32_t B, int32_t K, int32_t H,
+                int32_t root_joint, void* stream) {
+  if (!h || !preds || !gt || !perr || B < 1 || K < 1 || H < 1 || root_joint >= kJ)
+    return fail(h, D3DP_E_INVALID, "pmpjpe: bad argument");
+  ProcrustesParams p{preds, gt, perr, B, K, H, h->cfg.frames, root_joint};
+  const long long n = static_cast<long long>(B) * K * H * p.F;
+  const int blocks = static_cast<int>(std::min<long long>((n + 127) / 128, static_cast<long long>(h->num_sms) * 16));
+  procrustes_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  CK(cudaGetLastError());
+  return D3DP_OK;
+}
+
 int d3dp_jpma(d3dp_handle* h, const float* preds, const float* traj, const float* cam, const float* x2d,
               float* jagg_pose, int32_t* jagg_idx, float* pagg_pose, float* e2d_min, int32_t B, int32_t K, int32_t H,
               int32_t root_joint, int32_t linear, void* stream) {

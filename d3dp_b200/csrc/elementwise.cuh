@@ -433,4 +433,173 @@ __global__ void __launch_bounds__(256) jpma_kernel(const JpmaParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Protocol-2 errors: per-pose rigid alignment (scale, rotation, translation) of every hypothesis pose to the ground
+// truth, then the per-joint distance (reference: common/loss.py:190-259 p_mpjpe_diffusion_all_min, :261-330
+// p_mpjpe_diffusion, :332-395 p_mpjpe_diffusion_reproj — there a GPU -> numpy round trip with a batched LAPACK SVD).
+// One thread per pose (b,k,h,f).  With X = target, Y = prediction, X0/Y0 centred and Frobenius-normalised,
+// M = X0^T Y0 = U S V^T:  R = V diag(1,1,d) U^T with d = sign det(V U^T) = sign det(M),  a = (s1+s2+d s3) |X0|/|Y0|,
+// t = muX - a muY R,  aligned = a Y R + t.  The 3x3 SVD is a cyclic Jacobi eigen-decomposition of M^T M in float64
+// (V, s^2), u_i = M v_i / s_i for the two leading directions and u3 = u1 x u2 (the sign of u3 cancels in R).
+struct ProcrustesParams {
+  const float* pred;  // [B,K,H,F,17,3]
+  const float* gt;    // [B,F,17,3]
+  float* err;         // [B,K,H,F,17]
+  int B, K, H, F, root;
+};
+
+__device__ __forceinline__ void jacobi_rotate(double (&A)[3][3], double (&V)[3][3], int p, int q) {
+  if (fabs(A[p][q]) < 1e-300) return;
+  const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+  const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+  const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+  const int r = 3 - p - q;
+  const double app = A[p][p], aqq = A[q][q], apq = A[p][q], arp = A[r][p], arq = A[r][q];
+  A[p][p] = app - t * apq;
+  A[q][q] = aqq + t * apq;
+  A[p][q] = A[q][p] = 0.0;
+  A[r][p] = A[p][r] = c * arp - s * arq;
+  A[r][q] = A[q][r] = s * arp + c * arq;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double vp = V[i][p], vq = V[i][q];
+    V[i][p] = c * vp - s * vq;
+    V[i][q] = s * vp + c * vq;
+  }
+}
+
+__global__ void __launch_bounds__(128) procrustes_kernel(const ProcrustesParams p) {
+  const long long n = static_cast<long long>(p.B) * p.K * p.H * p.F;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int f = static_cast<int>(i % p.F);
+    const int b = static_cast<int>(i / (static_cast<long long>(p.F) * p.H * p.K));
+    const float* Yp = p.pred + i * (kJ * 3);
+    const float* Xp = p.gt + (static_cast<size_t>(b) * p.F + f) * (kJ * 3);
+    float Y[kJ][3], X[kJ][3];
+    double muX[3] = {0, 0, 0}, muY[3] = {0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < kJ; ++j)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        Y[j][c] = j == p.root ? 0.f : Yp[j * 3 + c];
+        X[j][c] = Xp[j * 3 + c];
+        muX[c] += X[j][c];
+        muY[c] += Y[j][c];
+      }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { muX[c] /= kJ; muY[c] /= kJ; }
+    double nX = 0, nY = 0, M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+    for (int j = 0; j < kJ; ++j) {
+      double x0[3], y0[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        x0[c] = X[j][c] - muX[c];
+        y0[c] = Y[j][c] - muY[c];
+        nX += x0[c] * x0[c];
+        nY += y0[c] * y0[c];
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) M[a][c] += x0[a] * y0[c];
+    }
+    nX = sqrt(nX);
+    nY = sqrt(nY);
+    const double inv = 1.0 / (nX * nY);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) M[a][c] *= inv;
+    // A = M^T M = V S^2 V^T
+    double A[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) A[a][c] = M[0][a] * M[0][c] + M[1][a] * M[1][c] + M[2][a] * M[2][c];
+    for (int sweep = 0; sweep < 8; ++sweep) {
+      jacobi_rotate(A, V, 0, 1);
+      jacobi_rotate(A, V, 0, 2);
+      jacobi_rotate(A, V, 1, 2);
+    }
+    // order the eigenpairs by descending eigenvalue
+    int o0 = 0, o1 = 1, o2 = 2;
+    if (A[o0][o0] < A[o1][o1]) { const int t_ = o0; o0 = o1; o1 = t_; }
+    if (A[o0][o0] < A[o2][o2]) { const int t_ = o0; o0 = o2; o2 = t_; }
+    if (A[o1][o1] < A[o2][o2]) { const int t_ = o1; o1 = o2; o2 = t_; }
+    const int ord[3] = {o0, o1, o2};
+    double sv[3], Vs[3][3];  // Vs[:, k] = k-th right singular vector
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      sv[k] = sqrt(fmax(A[ord[k]][ord[k]], 0.0));
+#pragma unroll
+      for (int a = 0; a < 3; ++a) Vs[a][k] = V[a][ord[k]];
+    }
+    double U[3][3];  // U[:, k]
+    {
+      double u1[3], u2[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        u1[a] = M[a][0] * Vs[0][0] + M[a][1] * Vs[1][0] + M[a][2] * Vs[2][0];
+        u2[a] = M[a][0] * Vs[0][1] + M[a][1] * Vs[1][1] + M[a][2] * Vs[2][1];
+      }
+      double n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+      if (n1 < 1e-150) { u1[0] = 1; u1[1] = 0; u1[2] = 0; n1 = 1; }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) u1[a] /= n1;
+      const double d12 = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) u2[a] -= d12 * u1[a];
+      double n2 = sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
+      if (n2 < 1e-150) {  // rank-1 M (collinear joints): any unit vector orthogonal to u1
+        const int m = fabs(u1[0]) <= fabs(u1[1]) ? (fabs(u1[0]) <= fabs(u1[2]) ? 0 : 2) : (fabs(u1[1]) <= fabs(u1[2]) ? 1 : 2);
+        double e[3] = {0, 0, 0};
+        e[m] = 1;
+        const double de = u1[m];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) u2[a] = e[a] - de * u1[a];
+        n2 = sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) u2[a] /= n2;
+      U[0][0] = u1[0]; U[1][0] = u1[1]; U[2][0] = u1[2];
+      U[0][1] = u2[0]; U[1][1] = u2[1]; U[2][1] = u2[2];
+      U[0][2] = u1[1] * u2[2] - u1[2] * u2[1];
+      U[1][2] = u1[2] * u2[0] - u1[0] * u2[2];
+      U[2][2] = u1[0] * u2[1] - u1[1] * u2[0];
+    }
+    const double detV = Vs[0][0] * (Vs[1][1] * Vs[2][2] - Vs[1][2] * Vs[2][1]) -
+                        Vs[0][1] * (Vs[1][0] * Vs[2][2] - Vs[1][2] * Vs[2][0]) +
+                        Vs[0][2] * (Vs[1][0] * Vs[2][1] - Vs[1][1] * Vs[2][0]);
+    const double detM = M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) -
+                        M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
+                        M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+    const double sg = detV >= 0.0 ? 1.0 : -1.0;  // with det U = +1 by construction: makes det R = +1
+    const double d = detM >= 0.0 ? 1.0 : -1.0;
+    double R[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) R[a][c] = Vs[a][0] * U[c][0] + Vs[a][1] * U[c][1] + sg * Vs[a][2] * U[c][2];
+    const double scale = (sv[0] + sv[1] + d * sv[2]) * nX / nY;
+    double t[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) t[c] = muX[c] - scale * (muY[0] * R[0][c] + muY[1] * R[1][c] + muY[2] * R[2][c]);
+    float* eo = p.err + i * kJ;
+#pragma unroll
+    for (int j = 0; j < kJ; ++j) {
+      double e2 = 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double al = scale * (Y[j][0] * R[0][c] + Y[j][1] * R[1][c] + Y[j][2] * R[2][c]) + t[c];
+        const double dd = al - X[j][c];
+        e2 += dd * dd;
+      }
+      eo[j] = static_cast<float>(sqrt(e2));
+    }
+  }
+}
+
+
 }  // namespace d3dp

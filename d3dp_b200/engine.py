@@ -163,6 +163,21 @@ class Engine:
                 ptr(e2d), ptr(e3d), ptr(jbest), B, K, H, int(root_joint), int(linear), _stream()), "d3dp_jpma_gt")
         return {"jagg_pose": jagg, "jagg_idx": idx, "pagg_pose": pagg, "e2d_min": e2d, "e3d": e3d, "jbest_pose": jbest}
 
+    def pmpjpe(self, preds, gt, root_joint=0):
+        """Procrustes-aligned per-joint errors (Protocol 2): preds [B,K,H,F,17,3] (or [B,K,F,17,3], e.g. the P-Agg
+        pose) vs gt [B,F,17,3] -> same leading shape + [17]."""
+        preds, gt = self._f32(preds), self._f32(gt)
+        squeeze = preds.dim() == 5
+        if squeeze:
+            preds = preds[:, :, None]
+        B, K, H = preds.shape[:3]
+        assert preds.shape[3:] == (self.frames, 17, 3) and gt.shape == (B, self.frames, 17, 3)
+        err = torch.empty(B, K, H, self.frames, 17, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.handle, self.lib.d3dp_pmpjpe(self.handle, ptr(preds), ptr(gt), ptr(err), B, K, H, int(root_joint),
+                                                    _stream()), "d3dp_pmpjpe")
+        return err[:, :, 0] if squeeze else err
+
     def philox_normal(self, B, H, per_bh, seed, h_offset=0, H_total=None, draw=0):
         out = torch.empty(B, H, per_bh, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):

@@ -121,6 +121,14 @@ int d3dp_jpma_gt(d3dp_handle* h, const float* preds, const float* traj, const fl
                  const float* gt, float* jagg_pose, int32_t* jagg_idx, float* pagg_pose, float* e2d_min, float* e3d,
                  float* jbest_pose, int32_t B, int32_t K, int32_t H, int32_t root_joint, int32_t linear, void* stream);
 
+/* Protocol-2 (Procrustes-aligned) per-joint errors (evaluation only; common/loss.py:190-395 p_mpjpe_diffusion_all_min,
+ * p_mpjpe_diffusion, p_mpjpe_diffusion_reproj — there a device->numpy round trip with a batched LAPACK SVD):
+ * every pose preds[b,k,h,f] (root joint zeroed on read when root_joint >= 0) is rigidly aligned (scale, rotation,
+ * translation) to gt[b,f] and perr[B,K,H,F,17] receives the per-joint distance after alignment.  Call with H = 1 on
+ * pagg_pose [B,K,F,17,3] for the P-Agg variant (mean_pos=True).  float64 3x3 Jacobi SVD per pose. */
+int d3dp_pmpjpe(d3dp_handle* h, const float* preds, const float* gt, float* perr, int32_t B, int32_t K, int32_t H,
+                int32_t root_joint, void* stream);
+
 /* Standard-normal Philox fill used for the sampler's noise, exposed so callers/tests can reproduce it:
  * out[B,H,per_bh] for draw index `draw`, hypotheses h_offset..h_offset+H-1 of H_total. */
 int d3dp_philox_normal(d3dp_handle* h, float* out, int32_t B, int32_t H, int64_t per_bh, uint64_t seed,

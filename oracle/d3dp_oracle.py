@@ -239,6 +239,44 @@ def jpma_errors(preds, gt, traj, cam, x2d, root_joint=0, linear=False):
     return {"J-Best": j_best, "P-Best": p_best, "P-Agg": p_agg, "J-Agg": j_agg, "e3d": e3d, "jbest_pose": jbest_pose}
 
 
+def procrustes_errors(pred, gt):
+    """Per-joint distance after the rigid alignment of common/loss.py:208-238 (shared by the three p_mpjpe_* variants):
+    pred [..., 17, 3] poses, gt broadcastable to it.  float64 torch.linalg.svd instead of numpy's float32 LAPACK."""
+    Y = pred.double().reshape(-1, J, 3)
+    X = gt.double().expand_as(pred).reshape(-1, J, 3)
+    muX, muY = X.mean(1, keepdim=True), Y.mean(1, keepdim=True)
+    X0, Y0 = X - muX, Y - muY
+    nX = X0.pow(2).sum((1, 2), keepdim=True).sqrt()
+    nY = Y0.pow(2).sum((1, 2), keepdim=True).sqrt()
+    M = (X0 / nX).transpose(1, 2) @ (Y0 / nY)
+    U, s, Vt = torch.linalg.svd(M)
+    V = Vt.transpose(1, 2).clone()
+    d = torch.sign(torch.linalg.det(V @ U.transpose(1, 2)))
+    V[:, :, -1] *= d[:, None]
+    s = s.clone()
+    s[:, -1] *= d
+    R = V @ U.transpose(1, 2)
+    a = s.sum(1)[:, None, None] * nX / nY
+    t = muX - a * (muY @ R)
+    aligned = a * (Y @ R) + t
+    return torch.norm(aligned - X, dim=-1).reshape(pred.shape[:-1]).float()
+
+
+def p_jpma_errors(preds, gt, jagg_idx, root_joint=0):
+    """Protocol-2 versions of the four logged errors (main.py:726-729): preds [B,K,H,F,17,3], gt [B,F,17,3] (root
+    zeroed), jagg_idx [B,K,F,17] = the reprojection argmin of jpma().  Returns [K] tensors + the per-pose errors."""
+    B, K, H, F = preds.shape[:4]
+    P = preds.clone()
+    P[:, :, :, :, root_joint] = 0
+    pe = procrustes_errors(P, gt.reshape(B, 1, 1, F, J, 3))                                      # [B,K,H,F,17]
+    pe_mean = procrustes_errors(P.mean(dim=2), gt.reshape(B, 1, F, J, 3))                        # [B,K,F,17]
+    j_best = pe.permute(1, 2, 0, 3, 4).min(dim=1).values.reshape(K, -1).mean(-1)
+    p_best = pe.permute(1, 2, 0, 3, 4).reshape(K, H, -1).mean(-1).min(dim=1).values
+    p_agg = pe_mean.permute(1, 0, 2, 3).reshape(K, -1).mean(-1)
+    j_agg = torch.gather(pe, 2, jagg_idx.long().unsqueeze(2)).permute(1, 2, 0, 3, 4).reshape(K, -1).mean(-1)
+    return {"J-Best": j_best, "P-Best": p_best, "P-Agg": p_agg, "J-Agg": j_agg, "pe3d": pe, "pe3d_mean": pe_mean}
+
+
 def eval_data_prepare(receptive_field, inputs_2d):
     """main.py:267-299 for one sequence [N,17,C]: ceil(N/F) clips, the last one = the last F frames; replicate-pad
     sequences shorter than F."""

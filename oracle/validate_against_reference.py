@@ -73,6 +73,22 @@ def main():
         same = torch.allclose(v, errs[k], atol=1e-6)
         print(f"{k:7s} ref {v.tolist()} oracle {errs[k].tolist()} {'ok' if same else 'MISMATCH'}")
         ok &= same
+    # Protocol 2 (Procrustes) — the reference goes through numpy float32 SVD; .cuda() calls are routed to CPU here
+    import common.loss as ref_loss
+    _cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        p2_refs = {"J-Best": ref_loss.p_mpjpe_diffusion_all_min(pred, gt), "P-Best": ref_loss.p_mpjpe_diffusion(pred, gt),
+                   "P-Agg": ref_loss.p_mpjpe_diffusion_all_min(pred, gt, mean_pos=True),
+                   "J-Agg": ref_loss.p_mpjpe_diffusion_reproj(pred, gt, rep, x2d)}
+    finally:
+        torch.Tensor.cuda = _cuda
+    p2 = orc.p_jpma_errors(ref, gt, idx)
+    for k, v in p2_refs.items():
+        v = torch.as_tensor(v)
+        same = torch.allclose(v.double(), p2[k].double(), atol=2e-6)
+        print(f"P2 {k:7s} ref {v.tolist()} oracle {p2[k].tolist()} {'ok' if same else 'MISMATCH'}")
+        ok &= same
     print("ORACLE PINNED" if ok else "ORACLE MISMATCH")
     return 0 if ok else 1
 

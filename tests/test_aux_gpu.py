@@ -165,9 +165,12 @@ def test_jpma_metrics_match_oracle():
     x2d = 0.3 * torch.randn(B, F, 17, 2, generator=g)
     traj, cam = synthetic_camera(B, F)
     ref = orc.jpma_errors(preds, gt, traj, cam, x2d)
-    out = jpma_metrics(_engine(F), preds, gt, traj, cam, x2d)
+    out = jpma_metrics(_engine(F), preds, gt, traj, cam, x2d, protocol2=True)
+    ref2 = orc.p_jpma_errors(preds, gt, out["jagg_idx"].cpu())
     for k in ("J-Best", "P-Best", "P-Agg", "J-Agg"):
         assert torch.allclose(out[k].cpu(), ref[k], atol=2e-6), k
+        assert torch.allclose(out["P2-" + k].cpu(), ref2[k], atol=2e-6), k       # main.py:726-729
+    assert torch.allclose(out["pe3d"].cpu(), ref2["pe3d"], atol=1e-6)
     assert torch.allclose(out["e3d"].cpu(), ref["e3d"], atol=1e-6)
     assert torch.equal(out["jbest_pose"].cpu()[..., 1:, :], ref["jbest_pose"][..., 1:, :])
     assert (out["J-Best"] <= out["J-Agg"] + 1e-6).all() and (out["J-Best"] <= out["P-Best"] + 1e-6).all()
@@ -188,3 +191,59 @@ def test_3dhp_variant_outputs_millimetres():
     assert torch.equal(out, base * 1000)  # same chain, one extra float32 multiply per stored value
     mean, mx = mpjpe_distance(out / 1000, case["preds"])
     assert mean < 1e-3
+
+
+def test_pmpjpe_kernel_matches_oracle():
+    """procrustes_kernel (float64 Jacobi SVD per pose) vs torch.linalg.svd restatement of common/loss.py:208-238,
+    including mirrored poses (the det(R) = -1 branch), a far-off pose, and the H = 1 (P-Agg) call form."""
+    g = torch.Generator().manual_seed(3)
+    B, K, H, F = 2, 3, 5, 27
+    gt = 0.4 * torch.randn(B, F, 17, 3, generator=g)
+    gt[:, :, 0] = 0
+    preds = gt[:, None, None] + 0.3 * torch.randn(B, K, H, F, 17, 3, generator=g)
+    preds[0, 0, 0] *= torch.tensor([-1.0, 1.0, 1.0])         # reflection
+    preds[1, 1, 1] = torch.randn(F, 17, 3, generator=g)      # unrelated pose
+    preds[1, 2, 3] = 1000.0 * gt[1] + 5.0                    # scaled + shifted copy: error ~ 0 after alignment
+    eng = _engine(F)
+    err = eng.pmpjpe(preds, gt, root_joint=0).cpu()
+    P = preds.clone()
+    P[:, :, :, :, 0] = 0
+    ref = orc.procrustes_errors(P, gt.reshape(B, 1, 1, F, 17, 3))
+    assert torch.allclose(err, ref, atol=1e-6)
+    assert err[1, 2, 3, :, 1:].max() < 0.3                   # root was zeroed -> not an exact copy, but close
+    exact = eng.pmpjpe((1000.0 * gt + 5.0)[:, None], gt, root_joint=-1).cpu()   # [B,1,F,17,3] form
+    assert exact.shape == (B, 1, F, 17) and exact.max() < 1e-5
+
+
+def test_sequence_evaluator_on_device():
+    """evaluate_sequences with the real kernels: packed and per-sequence batching agree (deterministic stand-in
+    sampler), and the full path (sampler + JPMA + P1/P2 metrics + stitched poses) runs from ragged sequences."""
+    from d3dp_b200.evaluate import evaluate_sequences
+    from tests.util import make_args
+    from d3dp_b200 import D3DP
+    F, K, H = 27, 2, 3
+    torch.manual_seed(0)
+    model = D3DP(make_args(F, depth=2), JL, JR, is_train=False, num_proposals=H, sampling_timesteps=K).cuda().eval()
+    g = torch.Generator().manual_seed(1)
+    seqs = []
+    for n in (11, 60, 81):
+        gt = 0.3 * torch.randn(n, 17, 3, generator=g) + torch.tensor([0.0, 0.0, 4.0])
+        seqs.append({"x2d": 0.3 * torch.randn(n, 17, 2, generator=g), "gt": gt,
+                     "cam": torch.tensor([1.1, 1.1, 0.01, -0.02, -0.2, 0.1, 0.0, 0.001, -0.001])})
+
+    def fake(xb, fb, bi):
+        base = torch.cat([xb, xb[..., :1] * 0.5], dim=-1)[:, None, None]
+        hk = (torch.arange(K, device=xb.device).reshape(1, K, 1, 1, 1, 1) * 0.01 +
+              torch.arange(H, device=xb.device).reshape(1, 1, H, 1, 1, 1) * 0.02)
+        return (base + hk * (1 + fb[..., :1][:, None, None])).contiguous()
+
+    kw = dict(kps_left=JL, kps_right=JR, batch_size=2, protocol2=True)
+    a = evaluate_sequences(model, seqs, packed=True, sampler=fake, **kw)
+    b = evaluate_sequences(model, seqs, packed=False, sampler=fake, **kw)
+    assert a["n_batches"] == 4 and b["n_batches"] == 1 + 2 + 2
+    for k in ("J-Best", "P-Best", "P-Agg", "J-Agg"):
+        assert torch.allclose(a[k], b[k], atol=1e-6) and torch.allclose(a["P2-" + k], b["P2-" + k], atol=1e-6), k
+    full = evaluate_sequences(model, seqs, packed=True, seed=7, return_poses=True, **kw)
+    assert all(torch.isfinite(full[k]).all() for k in ("J-Best", "P-Best", "P-Agg", "J-Agg", "P2-J-Agg"))
+    assert (full["J-Best"] <= full["J-Agg"] + 1e-6).all() and (full["P2-J-Best"] <= full["P2-P-Best"] + 1e-6).all()
+    assert [tuple(p.shape) for p in full["jagg_pose"]] == [(K, 11, 17, 3), (K, 60, 17, 3), (K, 81, 17, 3)]

@@ -154,3 +154,83 @@ def test_3dhp_variant_surface():
     from tests.util import JL, JR, make_args
     m = D3DP3(make_args(9, depth=1), JL, JR, is_train=False, num_proposals=1, sampling_timesteps=1)
     assert m.OUTPUT_SCALE == 1000.0 and m.pose_estimator._output_scale == 1000.0 and len(m.state_dict()) == 12 + 40
+
+
+class _OracleEngine:
+    """Stand-in for Engine in host-logic tests: same jpma_gt / pmpjpe surface, computed by the oracle on CPU."""
+    device = torch.device("cpu")
+
+    def __init__(self, frames):
+        self.frames = frames
+
+    def jpma_gt(self, preds, traj, cam, x2d, gt, root_joint=0, linear=False):
+        from oracle import d3dp_oracle as orc
+        jagg, idx, pagg, e2d = orc.jpma(preds, traj, cam, x2d, root_joint, linear)
+        e = orc.jpma_errors(preds, gt, traj, cam, x2d, root_joint, linear)
+        return {"jagg_pose": jagg, "jagg_idx": idx.int(), "pagg_pose": pagg, "e2d_min": e2d, "e3d": e["e3d"],
+                "jbest_pose": e["jbest_pose"]}
+
+    def pmpjpe(self, preds, gt, root_joint=0):
+        from oracle import d3dp_oracle as orc
+        P = preds.clone()
+        if root_joint >= 0:
+            P[..., root_joint, :] = 0
+        g = gt[:, None, None] if preds.dim() == 6 else gt[:, None]
+        return orc.procrustes_errors(P, g)
+
+
+def test_sequence_evaluator_packing_keeps_reference_numbers():
+    """evaluate_sequences: packed cross-sequence batches give the numbers of the reference's per-sequence loop
+    (main.py:685-724: per batch errors weighted by B*F), including the batch-dependent P-Best."""
+    import types
+    from d3dp_b200.clips import eval_data_prepare, flip_inputs
+    from d3dp_b200.evaluate import evaluate_sequences
+    from d3dp_b200.synthetic import H36M_JOINTS_LEFT as JL, H36M_JOINTS_RIGHT as JR
+    from oracle import d3dp_oracle as orc
+    F, K, H, bs = 9, 2, 4, 3
+    eng = _OracleEngine(F)
+    model = types.SimpleNamespace(frames=F, pose_estimator=types.SimpleNamespace(engine=lambda: eng))
+    g = torch.Generator().manual_seed(0)
+    seqs = []
+    for n in (5, 31, 40, 9):
+        gt = 0.3 * torch.randn(n, 17, 3, generator=g) + torch.tensor([0.0, 0.0, 4.0])
+        x2d = 0.3 * torch.randn(n, 17, 2, generator=g)
+        seqs.append({"x2d": x2d, "gt": gt, "cam": torch.tensor([1.1, 1.1, 0.01, -0.02, -0.2, 0.1, 0.0, 0.001, -0.001])})
+
+    def fake_preds(xb, fb):  # deterministic per clip, hypothesis- and step-dependent
+        B = xb.shape[0]
+        base = torch.cat([xb, xb[..., :1] * 0.5], dim=-1)[:, None, None]                     # [B,1,1,F,17,3]
+        hk = torch.arange(K).reshape(1, K, 1, 1, 1, 1) * 0.01 + torch.arange(H).reshape(1, 1, H, 1, 1, 1) * 0.02
+        return base + hk * (1 + fb[..., :1][:, None, None])
+
+    kw = dict(kps_left=JL, kps_right=JR, batch_size=bs, protocol2=True, sampler=lambda xb, fb, bi: fake_preds(xb, fb))
+    packed = evaluate_sequences(model, seqs, packed=True, return_poses=True, **kw)
+    plain = evaluate_sequences(model, seqs, packed=False, **kw)
+    assert packed["n_clips"] == 1 + 4 + 5 + 1 and packed["n_batches"] == 4 and plain["n_batches"] == 1 + 2 + 2 + 1
+    # the reference loop, restated: per sequence, per batch of <= bs clips, errors weighted by B*F
+    tot = {k: torch.zeros(K, dtype=torch.float64) for k in ("J-Best", "P-Best", "P-Agg", "J-Agg")}
+    tot2 = {k: torch.zeros(K, dtype=torch.float64) for k in tot}
+    N = 0
+    for s in seqs:
+        a, gt_c = eval_data_prepare(F, s["x2d"][None], s["gt"][None])
+        b, _ = eval_data_prepare(F, flip_inputs(s["x2d"][None], JL, JR))
+        traj = gt_c[:, :, :1].clone()
+        gt_c = gt_c.clone()
+        gt_c[:, :, 0] = 0
+        for i in range(0, a.shape[0], bs):
+            xb, fb, gb, tb = a[i:i + bs], b[i:i + bs], gt_c[i:i + bs], traj[i:i + bs]
+            preds = fake_preds(xb, fb)
+            cam = s["cam"][None].expand(xb.shape[0], 9)
+            e = orc.jpma_errors(preds, gb, tb, cam, xb)
+            _, idx, _, _ = orc.jpma(preds, tb, cam, xb)
+            e2 = orc.p_jpma_errors(preds, gb, idx)
+            w = xb.shape[0] * F
+            for k in tot:
+                tot[k] += w * e[k].double()
+                tot2[k] += w * e2[k].double()
+            N += w
+    for k in tot:
+        for res in (packed, plain):
+            assert torch.allclose(res[k].double(), tot[k] / N, atol=1e-6), k
+            assert torch.allclose(res["P2-" + k].double(), tot2[k] / N, atol=1e-6), k
+    assert [p.shape[1] for p in packed["jagg_pose"]] == [5, 31, 40, 9] and packed["pagg_pose"][1].shape == (K, 31, 17, 3)
