@@ -46,21 +46,28 @@ constexpr int GEMM_BK = 64;  // 64 fp16 = one 128-byte swizzle row
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 64 + GEMM_EPI_WARPS * 32;
 
-// Exact-erf GELU (reference: nn.GELU() default, common/mixste.py:24,39) with erf by Abramowitz & Stegun 7.1.26
-// (|abs error| <= 1.5e-7, far below the fp16 rounding of the result), arranged for the epilogue's issue budget:
-// branch-free, 2 MUFU (rcp, ex2) + 12 FMA-pipe ops.  With zc = v * sqrt(log2 e / 2):  erf(|v|/sqrt 2) =
-// 1 - poly(t) * 2^(-zc^2),  t = 1 / (1 + (p / sqrt(log2 e)) |zc|);  gelu = v/2 + v/2 * sign(v) * erf(|v|/sqrt 2).
-__device__ __forceinline__ float gelu_erf(float v) {
-  const float zc = v * 0.84932180028801907f;                // v / sqrt(2) * sqrt(log2(e))
-  const float t = rcp_approx(fmaf(0.27273678890578706f, fabsf(zc), 1.0f));  // 0.3275911 / sqrt(log2(e))
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float r = fmaf(-poly, ex2_approx(-zc * zc), 1.0f);  // erf(|v| / sqrt 2)
-  const float hv = 0.5f * v;
-  return fmaf(hv, copysignf(r, v), hv);
+// Exact-erf GELU (reference: nn.GELU() default, common/mixste.py:24,39), two values per call, arranged for the
+// epilogue's pipe budget on sm_100 (MUFU: 16 lanes/clk/SM, so every MUFU op costs a warp 8 pipe cycles):
+//   gelu(v) = v Phi(v) = max(v, 0) - |v| Phi(-|v|),   Phi(-u) = erfc(u / sqrt 2) / 2 = 2^q(u),
+// q = degree-6 fit of log2 Phi(-u) on [0, 5.5] (u clamped there: Phi(-5.5) = 1.9e-8), weighted so that the error of
+// the result stays below 0.008 ulp of its fp16 rounding everywhere (max |abs error| 1e-6; measured against the fp64
+// erf form on 6M normal draws the fp16 results differ in 0.36 % of cases, vs 1.05 % for the Abramowitz-Stegun 7.1.26
+// form this replaces).  Cost per value: 1 MUFU (ex2) + 3.5 packed FFMA2 + 2 FMNMX, instead of 2 MUFU + 13 FMA-pipe ops;
+// the polynomial runs on negated arguments (w = -|v| = min(v, -v)), hence the alternating coefficient signs.
+__device__ __forceinline__ void gelu_erf_x2(float& a, float& b) {
+  const float wa = fminf(a, -a), wb = fminf(b, -b);
+  const uint64_t w = pack_f32x2(wa, wb);
+  const uint64_t u = pack_f32x2(fmaxf(wa, -5.5f), fmaxf(wb, -5.5f));
+  uint64_t q = fma_f32x2(u, dup_f32x2(3.298481413e-05f), dup_f32x2(7.550812989e-04f));
+  q = fma_f32x2(q, u, dup_f32x2(7.973053230e-03f));
+  q = fma_f32x2(q, u, dup_f32x2(5.311827015e-02f));
+  q = fma_f32x2(q, u, dup_f32x2(-4.591021916e-01f));
+  q = fma_f32x2(q, u, dup_f32x2(1.151066177e+00f));
+  q = fma_f32x2(q, u, dup_f32x2(-1.000005425e+00f));
+  float qa, qb;
+  unpack_f32x2(q, qa, qb);
+  const uint64_t g = fma_f32x2(w, pack_f32x2(ex2_approx(qa), ex2_approx(qb)), pack_f32x2(fmaxf(a, 0.f), fmaxf(b, 0.f)));
+  unpack_f32x2(g, a, b);
 }
 
 // tmA: A [M,K], box {64,128};  tmB: W [N,K], box {64,128} (half a weight slab);  tmC: out [M,N] fp16, box {64,128}
@@ -214,13 +221,10 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             uint32_t o[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float2 bb = *reinterpret_cast<const float2*>(sprm + n0 + c * 32 + 8 * i + 2 * q);
-              float a = __uint_as_float(v[8 * i + 2 * q]) + bb.x;
-              float b = __uint_as_float(v[8 * i + 2 * q + 1]) + bb.y;
-              if constexpr (EPI == EPI_BIAS_GELU_F16) {
-                a = gelu_erf(a);
-                b = gelu_erf(b);
-              }
+              float a, b;
+              unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[8 * i + 2 * q]), __uint_as_float(v[8 * i + 2 * q + 1])),
+                                     *reinterpret_cast<const uint64_t*>(sprm + n0 + c * 32 + 8 * i + 2 * q)), a, b);
+              if constexpr (EPI == EPI_BIAS_GELU_F16) gelu_erf_x2(a, b);
               o[q] = pack_half2(a, b);
             }
             const int piece = cc * 4 + i;

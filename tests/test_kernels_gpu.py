@@ -36,6 +36,25 @@ def test_gemm_bias_modes(M, mode):
     assert (out - ref).abs().mean().item() < 2e-3
 
 
+def test_gemm_gelu_epilogue_is_exact_erf_to_fp16_rounding():
+    """fc1's fused GELU (gelu_erf_x2: max(v,0) - |v| 2^q(|v|), degree-6 q) against float64 erf-GELU of the float64
+    pre-activation: the only error left is the fp16 rounding of the stored value (rel 2^-11) plus fp32 accumulation
+    noise, over pre-activations spanning +-8 (beyond the +-5.5 clamp of the fit) — mixste.py:24,39."""
+    eng = _engine(27)
+    g = torch.Generator().manual_seed(11)
+    M, K, N = 600, 512, 1024
+    a = torch.randn(M, K, generator=g).half()
+    w = (torch.randn(N, K, generator=g) * 0.05).half()
+    bias = 2.5 * torch.randn(N, generator=g)
+    pre = a.double() @ w.double().t() + bias.double()
+    assert pre.min() < -7 and pre.max() > 7
+    ref = 0.5 * pre * (1 + torch.erf(pre / math.sqrt(2)))
+    out = eng.test_gemm(1, a.cuda(), w.cuda(), bias.cuda()).double().cpu()
+    tol = 6e-4 * ref.abs() + 5e-6
+    assert ((out - ref).abs() <= tol).all(), ((out - ref).abs() - tol).max().item()
+    assert (out[pre < -6.5].abs() < 1e-6).all() and torch.allclose(out[pre > 6.5], pre[pre > 6.5], rtol=6e-4)
+
+
 @pytest.mark.parametrize("M", [128, 27 * 17 * 3, 128 * 149 + 5])
 @pytest.mark.parametrize("mode", [2, 3])
 @pytest.mark.parametrize("K", [512, 1024])
