@@ -8,6 +8,13 @@
 // warpgroup owns one TMEM lane (= query row) per thread: max, exp2, row sum, P -> fp16 written back over S in TMEM;
 // O = P.V is a TS-form tcgen05.mma (A = P from TMEM, B = V from smem, MN-major); O / rowsum is stored as fp16.
 // F <= 256 so one N tile holds the whole row: no online-softmax rescaling.
+//
+// Schedule (F > 128, two query tiles per item): the softmax is MUFU-bound (rows x keys ex2 at 16/clk/SM = 4096 clk per
+// item) and the two MMA phases leave the MUFU idle, so the single MMA thread issues the two query tiles of an item half
+// a period apart — S0(i), PV1(i-1), S1(i), PV0(i) — and warpgroup 0 runs its softmax while the tensor core works for
+// warpgroup 1 and vice versa (ping-pong), instead of both warpgroups exponentiating at once and then both waiting.
+// Q/K and V have their own full/empty barriers per stage: Q and K are released as soon as S1(i) has been issued, V
+// after PV1(i), which gives the TMA producer a full item period of prefetch distance with two 96 KB stages.
 #pragma once
 #include "ptx.cuh"
 
@@ -19,6 +26,7 @@ struct AttnTParams {
   int rows;      // F rounded up to a multiple of 16 (TMA box rows, UMMA N for S, K extent for P.V)
   __half* out;   // [T, 512] fp16
   float scale_log2e;  // head_dim^-0.5 * log2(e)
+  int lockstep;       // A/B knob (D3DP_ATTN_LOCKSTEP=1): issue S0,S1,PV0,PV1 per item instead of the ping-pong order
 };
 
 constexpr int ATT_TILE_BYTES = 256 * 128;          // room for 256 rows x 64 fp16
@@ -26,14 +34,39 @@ constexpr int ATT_STAGE_BYTES = 3 * ATT_TILE_BYTES;  // Q, K, V
 constexpr int ATT_STAGES = 2;
 constexpr int ATT_SMEM_BYTES = ATT_STAGES * ATT_STAGE_BYTES + 256 + 1024;
 
-// barriers: full[2], empty[2], s_full[2], p_full[2], o_full[2], s_free[2]
+// 2^x for a pair of non-positive arguments on the FMA pipes (no MUFU): round-to-nearest split x = n + f with the
+// 1.5*2^23 magic constant, degree-4 minimax polynomial for 2^f on [-0.5, 0.5] (rel. error 2.6e-6, two orders below the
+// fp16 rounding of P), exponent patched in with one integer shift-add.  Arguments are clamped at -125 (2^-125 ~ 0).
+__device__ __forceinline__ void ex2_poly_x2(float& a, float& b) {
+  const uint64_t x = pack_f32x2(fmaxf(a, -125.f), fmaxf(b, -125.f));
+  const uint64_t t = add_f32x2(x, dup_f32x2(12582912.f));
+  const uint64_t n = add_f32x2(t, dup_f32x2(-12582912.f));
+  const uint64_t f = fma_f32x2(n, dup_f32x2(-1.f), x);
+  uint64_t q = fma_f32x2(f, dup_f32x2(9.570096374e-03f), dup_f32x2(5.591785989e-02f));
+  q = fma_f32x2(q, f, dup_f32x2(2.402474496e-01f));
+  q = fma_f32x2(q, f, dup_f32x2(6.931218148e-01f));
+  q = fma_f32x2(q, f, dup_f32x2(9.999992614e-01f));
+  float qa, qb, ta, tb;
+  unpack_f32x2(q, qa, qb);
+  unpack_f32x2(t, ta, tb);
+  a = __uint_as_float(__float_as_uint(qa) + (__float_as_uint(ta) << 23));
+  b = __uint_as_float(__float_as_uint(qb) + (__float_as_uint(tb) << 23));
+}
+
+// barriers: qk_full[2], qk_empty[2], v_full[2], v_empty[2] (per smem stage); s_full[2], p_full[2], o_full[2],
+// s_free[2] (per query tile / TMEM region)
+// POLY: 2 of every 5 element pairs of a full key chunk take ex2_poly_x2 instead of MUFU.EX2, which balances the MUFU
+// (8 pipe cycles per warp instruction) against the FMA pipes (7 per pair-instruction sequence).
+template <int POLY>
 __global__ void __launch_bounds__(320, 1)
 attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + ATT_STAGES * ATT_STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + 2;
-  uint64_t* sfull_bar = empty_bar + 2;
+  uint64_t* qkfull_bar = reinterpret_cast<uint64_t*>(smem + ATT_STAGES * ATT_STAGE_BYTES);
+  uint64_t* qkempty_bar = qkfull_bar + 2;
+  uint64_t* vfull_bar = qkempty_bar + 2;
+  uint64_t* vempty_bar = vfull_bar + 2;
+  uint64_t* sfull_bar = vempty_bar + 2;
   uint64_t* pfull_bar = sfull_bar + 2;
   uint64_t* ofull_bar = pfull_bar + 2;
   uint64_t* sfree_bar = ofull_bar + 2;
@@ -47,8 +80,10 @@ attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParam
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&qkfull_bar[i], 1);
+      mbar_init(&qkempty_bar[i], 1);
+      mbar_init(&vfull_bar[i], 1);
+      mbar_init(&vempty_bar[i], 1);
       mbar_init(&sfull_bar[i], 1);
       mbar_init(&pfull_bar[i], 4);
       mbar_init(&ofull_bar[i], 1);
@@ -66,16 +101,18 @@ attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParam
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t bytes = 3u * p.rows * 128u;
+      const uint32_t tile_bytes = p.rows * 128u;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int seq = item >> 3, head = item & 7;
-        mbar_wait_backoff(&empty_bar[s], ph ^ 1);
         uint8_t* st = smem + s * ATT_STAGE_BYTES;
-        mbar_expect_tx(&full_bar[s], bytes);
         const int row0 = seq * p.F;
-        tma_load_2d(st, &tmQKV, &full_bar[s], head * 64, row0);
-        tma_load_2d(st + ATT_TILE_BYTES, &tmQKV, &full_bar[s], 512 + head * 64, row0);
-        tma_load_2d(st + 2 * ATT_TILE_BYTES, &tmQKV, &full_bar[s], 1024 + head * 64, row0);
+        mbar_wait_backoff(&qkempty_bar[s], ph ^ 1);
+        mbar_expect_tx(&qkfull_bar[s], 2u * tile_bytes);
+        tma_load_2d(st, &tmQKV, &qkfull_bar[s], head * 64, row0);
+        tma_load_2d(st + ATT_TILE_BYTES, &tmQKV, &qkfull_bar[s], 512 + head * 64, row0);
+        mbar_wait_backoff(&vempty_bar[s], ph ^ 1);
+        mbar_expect_tx(&vfull_bar[s], tile_bytes);
+        tma_load_2d(st + 2 * ATT_TILE_BYTES, &tmQKV, &vfull_bar[s], 1024 + head * 64, row0);
         if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
       }
     }
@@ -84,40 +121,103 @@ attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParam
       const uint32_t idesc_s = make_idesc_f16(128, p.rows, 0, 0);  // S = Q.K^T : both K-major
       const uint32_t idesc_o = make_idesc_f16(128, 64, 0, 1);      // O = P.V   : A from TMEM, B (V) MN-major
       const int pv_ksteps = p.rows / 16;
-      int s = 0;
-      uint32_t ph = 0, iph = 0;  // iph: per-item phase of the s/p/o barriers
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t q_base = smem_u32(smem + s * ATT_STAGE_BYTES);
-        const uint32_t k_base = q_base + ATT_TILE_BYTES;
-        const uint32_t v_base = q_base + 2 * ATT_TILE_BYTES;
-        for (int mt = 0; mt < n_mtiles; ++mt) {
-          mbar_wait(&sfree_bar[mt], iph ^ 1);  // previous item's O of this region has been read out
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + mt * 256;
+      auto issue_s = [&](int mt, uint32_t stage_base) {  // S(mt) = Q[mt].K^T -> TMEM region mt, columns [0, rows)
+        const uint32_t d_tmem = tmem_base + mt * 256;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = make_sdesc_sw128(q_base + mt * 128 * 128 + k * 32, 16, 1024);
-            const uint64_t bdesc = make_sdesc_sw128(k_base + k * 32, 16, 1024);
-            mma_f16_ss(d_tmem, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
-          }
-          tc_commit(&sfull_bar[mt]);
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t adesc = make_sdesc_sw128(stage_base + mt * 128 * 128 + k * 32, 16, 1024);
+          const uint64_t bdesc = make_sdesc_sw128(stage_base + ATT_TILE_BYTES + k * 32, 16, 1024);
+          mma_f16_ss(d_tmem, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
         }
-        for (int mt = 0; mt < n_mtiles; ++mt) {
-          mbar_wait(&pfull_bar[mt], iph);
+        tc_commit(&sfull_bar[mt]);
+      };
+      auto issue_pv = [&](int mt, uint32_t stage_base) {  // O(mt) = P(mt).V : P fp16 at columns [0,128), O at [128,192)
+        const uint32_t p_tmem = tmem_base + mt * 256;
+        const uint32_t o_tmem = p_tmem + 128;
+        const uint32_t v_base = stage_base + 2 * ATT_TILE_BYTES;
+        for (int k = 0; k < pv_ksteps; ++k)
+          mma_f16_ts(o_tmem, p_tmem + k * 8, make_sdesc_sw128(v_base + k * 16 * 128, 1024, 1024), idesc_o,
+                     k != 0 ? 1u : 0u);
+        tc_commit(&ofull_bar[mt]);
+      };
+      int s = 0;
+      uint32_t ph = 0, iph = 0;  // ph: phase of the stage barriers; iph: per-item phase of the s/p/o barriers
+      if (n_mtiles == 2 && p.lockstep) {
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+          const uint32_t base = smem_u32(smem + s * ATT_STAGE_BYTES);
+          mbar_wait(&qkfull_bar[s], ph);
+          for (int mt = 0; mt < 2; ++mt) {
+            mbar_wait(&sfree_bar[mt], iph ^ 1);
+            tc_fence_after();
+            issue_s(mt, base);
+          }
+          tc_commit(&qkempty_bar[s]);
+          mbar_wait(&vfull_bar[s], ph);
+          for (int mt = 0; mt < 2; ++mt) {
+            mbar_wait(&pfull_bar[mt], iph);
+            tc_fence_after();
+            issue_pv(mt, base);
+          }
+          tc_commit(&vempty_bar[s]);
+          if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
+          iph ^= 1;
+        }
+      } else if (n_mtiles == 1) {
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+          const uint32_t base = smem_u32(smem + s * ATT_STAGE_BYTES);
+          mbar_wait(&qkfull_bar[s], ph);
+          mbar_wait(&sfree_bar[0], iph ^ 1);  // previous item's O has been read out
           tc_fence_after();
-          const uint32_t p_tmem = tmem_base + mt * 256;        // P: fp16 pairs, columns [0,128)
-          const uint32_t o_tmem = tmem_base + mt * 256 + 128;  // O: fp32, columns [128,192)
-          for (int k = 0; k < pv_ksteps; ++k) {
-            const uint64_t bdesc = make_sdesc_sw128(v_base + k * 16 * 128, 1024, 1024);
-            mma_f16_ts(o_tmem, p_tmem + k * 8, bdesc, idesc_o, k != 0 ? 1u : 0u);
-          }
-          tc_commit(&ofull_bar[mt]);
+          issue_s(0, base);
+          tc_commit(&qkempty_bar[s]);
+          mbar_wait(&vfull_bar[s], ph);
+          mbar_wait(&pfull_bar[0], iph);
+          tc_fence_after();
+          issue_pv(0, base);
+          tc_commit(&vempty_bar[s]);
+          if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
+          iph ^= 1;
         }
-        tc_commit(&empty_bar[s]);  // all MMAs that read this smem stage are done
-        if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
-        iph ^= 1;
+      } else {
+        bool first = true;
+        uint32_t prev_base = 0;
+        int prev_s = 0;
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+          const uint32_t base = smem_u32(smem + s * ATT_STAGE_BYTES);
+          // S0(i)
+          mbar_wait(&qkfull_bar[s], ph);
+          mbar_wait(&sfree_bar[0], iph ^ 1);
+          tc_fence_after();
+          issue_s(0, base);
+          // PV1(i-1): V of the previous stage (its v_full was waited for before PV0(i-1))
+          if (!first) {
+            mbar_wait(&pfull_bar[1], iph ^ 1);
+            tc_fence_after();
+            issue_pv(1, prev_base);
+            tc_commit(&vempty_bar[prev_s]);
+          }
+          // S1(i)
+          mbar_wait(&sfree_bar[1], iph ^ 1);
+          tc_fence_after();
+          issue_s(1, base);
+          tc_commit(&qkempty_bar[s]);  // Q and K of this item are not read again
+          // PV0(i)
+          mbar_wait(&vfull_bar[s], ph);
+          mbar_wait(&pfull_bar[0], iph);
+          tc_fence_after();
+          issue_pv(0, base);
+          first = false;
+          prev_base = base;
+          prev_s = s;
+          if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
+          iph ^= 1;
+        }
+        if (!first) {  // PV1 of the last item
+          mbar_wait(&pfull_bar[1], iph ^ 1);
+          tc_fence_after();
+          issue_pv(1, prev_base);
+          tc_commit(&vempty_bar[prev_s]);
+        }
       }
     }
   } else {
@@ -176,8 +276,14 @@ attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParam
           if (c < full_chunks) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float a = ex2_approx(fmaf(__uint_as_float(v[2 * i]), p.scale_log2e, -moff));
-              const float b = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2e, -moff));
+              float a = fmaf(__uint_as_float(v[2 * i]), p.scale_log2e, -moff);
+              float b = fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2e, -moff);
+              if (POLY && (i % 5) < 2) {
+                ex2_poly_x2(a, b);
+              } else {
+                a = ex2_approx(a);
+                b = ex2_approx(b);
+              }
               sum += a + b;
               o[i] = pack_half2(a, b);
             }

@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -73,6 +74,12 @@ int fail(d3dp_handle* h, int code, const std::string& msg) {
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// A/B knobs for kernel experiments (read per launch so one process can time both settings)
+int env_flag(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e && e[0] ? (e[0] != '0') : dflt;
+}
 
 // 2-D row-major tensor map, 128-byte swizzle, box = {128 bytes of columns, box_rows}; fp16 (default) or fp32
 int make_tmap(d3dp_handle* h, CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
@@ -194,7 +201,8 @@ int ensure_attrs(d3dp_handle* h) {
   if ((rc = set_smem_attr(h, k_gemm_fc1, kSmemGemm))) return rc;
   if ((rc = set_smem_attr(h, k_gemm_proj, kSmemN512))) return rc;
   if ((rc = set_smem_attr(h, k_gemm_fc2, kSmemN512))) return rc;
-  if ((rc = set_smem_attr(h, attn_temporal_kernel, ATT_SMEM_BYTES))) return rc;
+  if ((rc = set_smem_attr(h, attn_temporal_kernel<0>, ATT_SMEM_BYTES))) return rc;
+  if ((rc = set_smem_attr(h, attn_temporal_kernel<1>, ATT_SMEM_BYTES))) return rc;
   if ((rc = set_smem_attr(h, attn_temporal_long_kernel, ATTL_SMEM_BYTES))) return rc;
   if ((rc = set_smem_attr(h, attn_spatial_kernel, SP_SMEM_BYTES))) return rc;
   h->attrs_set = true;
@@ -253,6 +261,7 @@ int launch_attn_temporal(d3dp_handle* h, const __half* qkv, __half* o16, int n_s
   p.rows = F <= 256 ? (F + 15) / 16 * 16 : (F + 31) / 32 * 32;  // long kernel: two halves, each a multiple of 16
   p.out = o16;
   p.scale_log2e = 0.125f * 1.4426950408889634f;
+  p.lockstep = env_flag("D3DP_ATTN_LOCKSTEP", 0);
   CUtensorMap tm;
   const bool is_long = F > 256;
   int rc = make_tmap(h, &tm, qkv, static_cast<uint64_t>(T), 1536, static_cast<uint32_t>(is_long ? p.rows / 2 : p.rows));
@@ -260,7 +269,8 @@ int launch_attn_temporal(d3dp_handle* h, const __half* qkv, __half* o16, int n_s
   const int items = p.num_seq * 8;
   const int grid = items < h->num_sms ? items : h->num_sms;
   if (is_long) attn_temporal_long_kernel<<<grid, 192, ATTL_SMEM_BYTES, st>>>(tm, p);
-  else attn_temporal_kernel<<<grid, 320, ATT_SMEM_BYTES, st>>>(tm, p);
+  else if (env_flag("D3DP_ATTN_POLY", 0)) attn_temporal_kernel<1><<<grid, 320, ATT_SMEM_BYTES, st>>>(tm, p);
+  else attn_temporal_kernel<0><<<grid, 320, ATT_SMEM_BYTES, st>>>(tm, p);
   CK(cudaGetLastError());
   return D3DP_OK;
 }
