@@ -261,7 +261,6 @@ int launch_attn_temporal(d3dp_handle* h, const __half* qkv, __half* o16, int n_s
   p.rows = F <= 256 ? (F + 15) / 16 * 16 : (F + 31) / 32 * 32;  // long kernel: two halves, each a multiple of 16
   p.out = o16;
   p.scale_log2e = 0.125f * 1.4426950408889634f;
-  p.lockstep = env_flag("D3DP_ATTN_LOCKSTEP", 0);
   CUtensorMap tm;
   const bool is_long = F > 256;
   int rc = make_tmap(h, &tm, qkv, static_cast<uint64_t>(T), 1536, static_cast<uint32_t>(is_long ? p.rows / 2 : p.rows));
