@@ -201,8 +201,7 @@ int ensure_attrs(d3dp_handle* h) {
   if ((rc = set_smem_attr(h, k_gemm_fc1, kSmemGemm))) return rc;
   if ((rc = set_smem_attr(h, k_gemm_proj, kSmemN512))) return rc;
   if ((rc = set_smem_attr(h, k_gemm_fc2, kSmemN512))) return rc;
-  if ((rc = set_smem_attr(h, attn_temporal_kernel<0>, ATT_SMEM_BYTES))) return rc;
-  if ((rc = set_smem_attr(h, attn_temporal_kernel<1>, ATT_SMEM_BYTES))) return rc;
+  if ((rc = set_smem_attr(h, attn_temporal_kernel, ATT_SMEM_BYTES))) return rc;
   if ((rc = set_smem_attr(h, attn_temporal_long_kernel, ATTL_SMEM_BYTES))) return rc;
   if ((rc = set_smem_attr(h, attn_spatial_kernel, SP_SMEM_BYTES))) return rc;
   h->attrs_set = true;
@@ -268,8 +267,7 @@ int launch_attn_temporal(d3dp_handle* h, const __half* qkv, __half* o16, int n_s
   const int items = p.num_seq * 8;
   const int grid = items < h->num_sms ? items : h->num_sms;
   if (is_long) attn_temporal_long_kernel<<<grid, 192, ATTL_SMEM_BYTES, st>>>(tm, p);
-  else if (env_flag("D3DP_ATTN_POLY", 0)) attn_temporal_kernel<1><<<grid, 320, ATT_SMEM_BYTES, st>>>(tm, p);
-  else attn_temporal_kernel<0><<<grid, 320, ATT_SMEM_BYTES, st>>>(tm, p);
+  else attn_temporal_kernel<<<grid, 320, ATT_SMEM_BYTES, st>>>(tm, p);
   CK(cudaGetLastError());
   return D3DP_OK;
 }
