@@ -75,12 +75,6 @@ int fail(d3dp_handle* h, int code, const std::string& msg) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// A/B knobs for kernel experiments (read per launch so one process can time both settings)
-int env_flag(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e && e[0] ? (e[0] != '0') : dflt;
-}
-
 // 2-D row-major tensor map, 128-byte swizzle, box = {128 bytes of columns, box_rows}; fp16 (default) or fp32
 int make_tmap(d3dp_handle* h, CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
               bool f32 = false) {
