@@ -10,12 +10,13 @@
 // in TMEM.  The kernel is a cta_group::2 GEMM: a CTA pair (cluster of 2) computes one 256x256 tile with a single MMA
 // stream (UMMA M=256, N=256, K=16).  Each CTA stages its own 128 A rows and HALF of the weight slab (128 of the 256
 // N rows) per k-block, so an SM reads 8 KB instead of 12 KB of operands from shared memory per MMA and fills 32 KB
-// instead of 48 KB by TMA — a single-CTA (M=128) version of this kernel measured shared-memory-bandwidth bound at
-// 56-60 % tensor-pipe utilisation; this one reaches 73 % (ncu) on the qkv shape.  The leader CTA (rank 0) issues all
-// MMAs; both CTAs' TMA loads complete on the leader's `full` barriers; MMA commits are multicast to both CTAs; each
-// CTA runs its own epilogue on its 128 rows.  Warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..9
-// = epilogue: TMEM lane == tile row, two 4-warp groups of 128 columns each; fp16 results are staged in
-// 128B-swizzled smem slabs and leave by TMA store.
+// instead of 48 KB by TMA.  The leader CTA (rank 0) issues all MMAs; both CTAs' TMA loads complete on the leader's
+// `full` barriers; MMA commits are multicast to both CTAs; each CTA runs its own epilogue on its 128 rows.
+// Warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..9 = epilogue: TMEM lane == tile row, two 4-warp
+// groups of 128 columns each; fp16 results are staged in 128B-swizzled smem slabs and leave by TMA store.
+// Template knobs: STAGES operand stages of 32 KB (the mainloop is bound by the bytes TMA keeps in flight: the tile
+// needs ~120 GB/s per SM at ~1.5 us of L2/HBM latency, i.e. ~180 KB), OUTBUFS output slabs per column split, and
+// BIAS_SMEM (bias staged in shared memory, or read through L1 when the smem is better spent on operand stages).
 #pragma once
 #include "ptx.cuh"
 
@@ -72,23 +73,23 @@ __device__ __forceinline__ void gelu_erf_x2(float& a, float& b) {
 
 // tmA: A [M,K], box {64,128};  tmB: W [N,K], box {64,128} (half a weight slab);  tmC: out [M,N] fp16, box {64,128}
 
-template <int STAGES>
+template <int STAGES, int OUTBUFS = 2, bool BIAS_SMEM = true>
 struct Gemm2SmSmem {
   static constexpr int A_BYTES = 128 * GEMM_BK * 2;       // this CTA's 128 rows of A
   static constexpr int B_BYTES = 128 * GEMM_BK * 2;       // this CTA's half (128 rows) of the 256-row weight slab
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;  // full[STAGES] empty[STAGES] tfull[2] tempty[2], tmem ptr
   static constexpr int PARAM_OFFSET = BAR_OFFSET + 256;
-  static constexpr int PARAM_FLOATS = 2560;
+  static constexpr int PARAM_FLOATS = BIAS_SMEM ? 1536 : 0;  // the whole bias vector (N <= 1536), or read through L1
   static constexpr int OUT_OFFSET = (PARAM_OFFSET + PARAM_FLOATS * 4 + 1023) / 1024 * 1024;
-  static constexpr int TOTAL = OUT_OFFSET + 2 * 2 * 16384 + 1024;
+  static constexpr int TOTAL = OUT_OFFSET + 2 * OUTBUFS * 16384 + 1024;  // [2 column splits][OUTBUFS] x 16 KB slabs
 };
 
-template <int EPI, int STAGES>
+template <int EPI, int STAGES, int OUTBUFS = 2, bool BIAS_SMEM = true>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-  using L = Gemm2SmSmem<STAGES>;
+  using L = Gemm2SmSmem<STAGES, OUTBUFS, BIAS_SMEM>;
   static_assert(EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16, "fp16-output epilogues only");
   constexpr int COLS_PER_THREAD = GEMM_BN / 2;
 
@@ -127,7 +128,9 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2sm<512>(tmem_ptr);
-  for (int i = threadIdx.x; i < p.N; i += blockDim.x) sprm[i] = p.bias[i];
+  if constexpr (BIAS_SMEM)
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) sprm[i] = p.bias[i];
+  const float* bias_src = BIAS_SMEM ? sprm : p.bias;  // generic loads: ld.shared or ld.global (L1 broadcast)
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -185,7 +188,7 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int split = ew >> 2;
     const int r = quad * 32 + lane;
     const int col0 = split * COLS_PER_THREAD;
-    uint8_t* gbuf = smem + L::OUT_OFFSET + split * 2 * 16384;
+    uint8_t* gbuf = smem + L::OUT_OFFSET + split * OUTBUFS * 16384;
     const bool leader = (ew & 3) == 0 && lane == 0;
     const uint32_t tempty_leader0 = mapa_u32(smem_u32(&tempty_bar[0]), 0);
     int as = 0;
@@ -198,13 +201,13 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int n0 = n_blk * GEMM_BN + col0;
 #pragma unroll 1
       for (int sl = 0; sl < COLS_PER_THREAD / 64; ++sl) {
-        uint8_t* buf = gbuf + (sl & 1) * 16384;
+        uint8_t* buf = gbuf + (sl % OUTBUFS) * 16384;
         // both 32-column chunks of the slab are read from TMEM before any math (one exposed TMEM latency per slab,
         // overlapped with the wait for the staging buffer)
         uint32_t v0[32], v1[32];
         tmem_ld32(taddr + sl * 64, v0);
         tmem_ld32(taddr + sl * 64 + 32, v1);
-        if (leader) tma_store_wait_read<1>();
+        if (leader) tma_store_wait_read<OUTBUFS - 1>();
         named_bar_sync(2 + split, 128);
         tmem_ld_wait();
         if (sl == COLS_PER_THREAD / 64 - 1) {  // all accumulator columns of this thread are in registers: free the stage
@@ -223,7 +226,7 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int q = 0; q < 4; ++q) {
               float a, b;
               unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[8 * i + 2 * q]), __uint_as_float(v[8 * i + 2 * q + 1])),
-                                     *reinterpret_cast<const uint64_t*>(sprm + n0 + c * 32 + 8 * i + 2 * q)), a, b);
+                                     *reinterpret_cast<const uint64_t*>(bias_src + n0 + c * 32 + 8 * i + 2 * q)), a, b);
               if constexpr (EPI == EPI_BIAS_GELU_F16) gelu_erf_x2(a, b);
               o[q] = pack_half2(a, b);
             }
