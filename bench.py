@@ -248,7 +248,7 @@ def kernel_rooflines(eng, T, n_streams, peaks):
 KERNEL_MODEL = {"gemm_qkv": (4096, "tensor"), "gemm_fc1_gelu": (3072, "tensor"), "gemm_proj_res_ln": (6144, "hbm"),
                 "gemm_fc2_res_ln2": (7168, "hbm"), "attn_temporal": (4096, "hbm"), "attn_spatial": (4096, "hbm")}
 # DRAM bytes per launch measured with ncu (dram__bytes_read.sum + dram__bytes_write.sum, T = 660 960; profiles/)
-NCU_TRAFFIC = {"gemm_qkv": 2.65e9, "gemm_fc1_gelu": 1.97e9, "gemm_proj_res_ln": 4.0e9, "gemm_fc2_res_ln2": 4.68e9,
+NCU_TRAFFIC = {"gemm_qkv": 2.97e9, "gemm_fc1_gelu": 1.97e9, "gemm_proj_res_ln": 4.0e9, "gemm_fc2_res_ln2": 4.68e9,
                "attn_temporal": 2.68e9, "attn_spatial": 2.68e9}
 
 
