@@ -189,7 +189,7 @@ def run_reference_arm(args, rank):
         "e2e": {"value": value, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # ----------------------------------------------------------------------------------------------------- our arm
@@ -389,10 +389,20 @@ def run_ours(args, rank, world, local_rank):
                           f"B=1 H=20 K=1 F=243 flip, {t_s * 1e3:.0f} ms, scaled by B*K linearity"}
         except Exception as ex:  # never let the extra baseline break the bench line
             line["gpu_eager_baseline"] = {"error": str(ex)[:200]}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
+
+
+_OUT = sys.stdout  # where the one JSON line goes (see main)
 
 
 def main():
+    # stdout must carry exactly ONE JSON line, but libraries write to file descriptor 1 behind Python's back (NCCL
+    # prints its version banner there on the first communicator): keep a private handle on the real stdout for the
+    # JSON line and point fd 1 at stderr for everything else.
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

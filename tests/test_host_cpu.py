@@ -234,3 +234,21 @@ def test_sequence_evaluator_packing_keeps_reference_numbers():
             assert torch.allclose(res[k].double(), tot[k] / N, atol=1e-6), k
             assert torch.allclose(res["P2-" + k].double(), tot2[k] / N, atol=1e-6), k
     assert [p.shape[1] for p in packed["jagg_pose"]] == [5, 31, 40, 9] and packed["pagg_pose"][1].shape == (K, 31, 17, 3)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py --impl reference (the reference's CPU path, oracle port) runs without a GPU and stdout carries exactly
+    one JSON line with the contract's keys; everything else (library banners, warnings) is kept off stdout."""
+    import json
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "poses/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
