@@ -252,3 +252,34 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "poses/s" and d["value"] > 0 and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_gelu_polynomial_in_kernel_source_meets_its_accuracy_claim():
+    """The fc1 epilogue's erf-GELU (gelu_erf_x2 in gemm_tcgen05.cuh: max(v,0) + w 2^q(max(w,-5.5)), w = -|v|) is
+    re-evaluated here in float32 from the coefficients parsed out of the kernel source and compared with the float64
+    erf form (reference: nn.GELU(), common/mixste.py:24,39): |error| <= 1e-6 everywhere and at most 0.02 ulp of the
+    fp16 value the kernel stores."""
+    import numpy as np
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "d3dp_b200", "csrc",
+                            "gemm_tcgen05.cuh")).read()
+    body = src[src.index("void gelu_erf_x2"):]
+    body = body[:body.index("unpack_f32x2(g, a, b)")]
+    coef = [np.float32(c) for c in re.findall(r"dup_f32x2\((-?[0-9.]+e[-+][0-9]+)f\)", body)]
+    assert len(coef) == 7 and "fmaxf(wa, -5.5f)" in body
+    f32 = np.float32
+    v = np.concatenate([np.linspace(-9, 9, 400001), np.random.default_rng(0).normal(size=400000)]).astype(f32)
+    w = np.minimum(v, -v)
+    u = np.maximum(w, f32(-5.5))
+    q = (u * coef[0] + coef[1]).astype(f32)                 # Horner in the kernel's order
+    for c in coef[2:]:
+        q = (q * u + c).astype(f32)
+    e = np.exp2(q.astype(np.float64)).astype(f32)
+    got = (w * e + np.maximum(v, f32(0))).astype(f32).astype(np.float64)
+    vd = v.astype(np.float64)
+    ref = 0.5 * vd * (1.0 + torch.erf(torch.from_numpy(vd) / np.sqrt(2.0)).numpy())
+    err = np.abs(got - ref)
+    ulp16 = np.maximum(2.0 ** -24, 2.0 ** (np.floor(np.log2(np.maximum(np.abs(ref), 1e-30))) - 10))
+    assert err.max() <= 1e-6
+    inside = np.abs(vd) <= 5.5                               # the fitted range; beyond it the result is -|v| 1.9e-8
+    assert (err / ulp16)[inside].max() <= 0.02, (err / ulp16)[inside].max()
+    assert err[~inside].max() <= 2e-7
