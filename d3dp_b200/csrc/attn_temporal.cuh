@@ -42,7 +42,7 @@ constexpr int ATT_SMEM_BYTES = ATT_STAGES * ATT_STAGE_BYTES + 256 + 1024;
 __global__ void __launch_bounds__(320, 1)
 attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* qkfull_bar = reinterpret_cast<uint64_t*>(smem + ATT_STAGES * ATT_STAGE_BYTES);
   uint64_t* qkempty_bar = qkfull_bar + 2;
   uint64_t* vfull_bar = qkempty_bar + 2;
@@ -331,7 +331,7 @@ constexpr int ATTL_SMEM_BYTES = 3 * ATTL_TILE_BYTES + 256 + 1024;
 __global__ void __launch_bounds__(192, 1)
 attn_temporal_long_kernel(const __grid_constant__ CUtensorMap tmQKV /* box {64, rows/2} */, const AttnTParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 3 * ATTL_TILE_BYTES);
   uint64_t* empty_bar = full_bar + 1;
   uint64_t* sfull_bar = empty_bar + 1;

@@ -94,7 +94,7 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   constexpr int COLS_PER_THREAD = GEMM_BN / 2;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);  // used in the leader only
   uint64_t* empty_bar = full_bar + STAGES;                                  // per CTA
   uint64_t* tfull_bar = empty_bar + STAGES;                                 // per CTA

@@ -215,6 +215,18 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return r;
 }
 
+// 1024-byte-aligned base of the dynamic shared memory (128B-swizzled TMA tiles need it).
+// Experiment switch -DD3DP_SMEM_PTRARITH=1 (default off, measured in round 2): rebuilding the pointer from an integer
+// discards the address space, so every later access through it is a generic LD/ST; pointer arithmetic on the
+// __shared__ array keeps it, and the same accesses compile to LDS/STS.  Same addresses either way.
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* raw) {
+#if defined(D3DP_SMEM_PTRARITH) && D3DP_SMEM_PTRARITH
+  return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+#else
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+#endif
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {  // whole warp
