@@ -63,8 +63,11 @@ def one():
             return (out,) if keep else None
         jobs.append((name, run))
 
+    only = [k for k in os.environ.get("AB_ONLY", "").split(",") if k]  # e.g. AB_ONLY=proj_res_ln,fc2_res_ln2
     parts = []
     for name, run in jobs:
+        if only and name not in only:
+            continue
         sums = [chk(t) for t in run(keep=True)]
         for _ in range(3):
             run()
@@ -89,6 +92,6 @@ if __name__ == "__main__":
         csrc = os.path.join(ROOT, "d3dp_b200", "csrc")
         libs = sys.argv[1:3] if len(sys.argv) >= 3 else ["libd3dp_b200.so", "ab_variant.so"]
         libs = [p if os.path.isabs(p) else os.path.join(csrc, p) for p in libs]
-        for lib in (libs[0], libs[1], libs[0], libs[1]):
+        for lib in (libs[0], libs[1]) * int(os.environ.get("AB_VISITS", "2")):
             subprocess.run([sys.executable, os.path.abspath(__file__), "one"], env=dict(os.environ, AB_LIB=lib),
                            timeout=300)
