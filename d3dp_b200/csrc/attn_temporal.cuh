@@ -37,6 +37,9 @@ constexpr int ATT_STAGE_BYTES = 3 * ATT_TILE_BYTES;  // Q, K, V
 constexpr int ATT_STAGES = 2;
 constexpr int ATT_SMEM_BYTES = ATT_STAGES * ATT_STAGE_BYTES + 256 + 1024;
 
+#if defined(D3DP_ATTN_SINGLE_READ) && D3DP_ATTN_SINGLE_READ
+#include "attn_temporal_sr.inc"
+#else
 // barriers: qk_full[2], qk_empty[2], v_full[2], v_empty[2] (per smem stage); s_full[2], p_full[2], o_full[2],
 // s_free[2] (per query tile / TMEM region)
 __global__ void __launch_bounds__(320, 1)
@@ -314,6 +317,8 @@ attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParam
     tmem_dealloc<512>(tmem_base);
   }
 }
+
+#endif
 
 }  // namespace d3dp
 
