@@ -292,11 +292,28 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       float t1 = 0.f, t2 = 0.f, py = 0.f;
       auto ln_a_chunk = [&](uint32_t (&v)[32], int c) {
         const int n = lcol0 + c * 32;
+#if defined(D3DP_TPOS_VEC) && D3DP_TPOS_VEC
+        // Experiment switch (default off, unmeasured): the thread's 32 Temporal_pos_embed values as four 256-bit
+        // loads instead of 32 scalar __ldg (row-per-thread: every warp load touches 32 rows = 32 L1 wavefronts;
+        // the S0 launch of fc2 measured 2.04 ms against 1.13-1.28 ms for the launches without the embedding).
+        uint32_t tp[32];
+        if constexpr (EPI == EPI_RES_LN2) {
+          if (p.tpos) {
+            const float* src = p.tpos + static_cast<size_t>(f) * 512 + ncol0 + n;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ldg256(src + 8 * q, *reinterpret_cast<uint32_t(*)[8]>(tp + 8 * q));
+          }
+        }
+#endif
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           float y = (__uint_as_float(v[i]) - mean) * rstd * sprm[256 + n + i] + sprm[512 + n + i];
           if constexpr (EPI == EPI_RES_LN2) {
+#if defined(D3DP_TPOS_VEC) && D3DP_TPOS_VEC
+            if (p.tpos) y += __uint_as_float(tp[i]);
+#else
             if (p.tpos) y += __ldg(p.tpos + static_cast<size_t>(f) * 512 + ncol0 + n + i);
+#endif
             if (c == 0 && i == 0) py = y;
             const float d = y - py;
             t1 += d;
