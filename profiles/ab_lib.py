@@ -82,6 +82,34 @@ def one():
             torch.cuda.synchronize()
             best = min(best, s.elapsed_time(e) / 10)
         parts.append(f"{name} {best:.4f} ms chk={sums}")
+    if not only or "sampler" in only:
+        # whole sampler at a small shape (covers embed / head / time-MLP / DDIM kernels in situ): time per call and the
+        # largest difference against the first build visited (variants that re-associate sums are not bit-identical)
+        from d3dp_b200 import D3DP
+        from d3dp_b200.synthetic import (H36M_JOINTS_LEFT as JL, H36M_JOINTS_RIGHT as JR, flip_2d,
+                                         synthetic_pose_estimator_state)
+        from tests.util import make_args
+        F, B, H, K = 243, 2, 10, 2
+        model = D3DP(make_args(F), JL, JR, is_train=False, num_proposals=H, sampling_timesteps=K)
+        model.pose_estimator.load_state_dict(synthetic_pose_estimator_state(F, seed=0), strict=True)
+        model = model.cuda().eval()
+        x2d = (0.3 * torch.randn(B, F, 17, 2, generator=torch.Generator().manual_seed(1234)))
+        x2f, x2d = flip_2d(x2d).cuda(), x2d.cuda()
+        out = model.ddim_sample_flip(x2d, None, input_2d_flip=x2f, seed=7)
+        torch.cuda.synchronize()
+        ref_path = os.path.join(os.environ.get("AB_TMP", "/tmp"), "ab_lib_sampler_ref.pt")
+        if os.path.exists(ref_path):
+            diff = (out.cpu() - torch.load(ref_path)).abs().max().item()
+        else:
+            torch.save(out.cpu(), ref_path)
+            diff = 0.0
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(3):
+            model.ddim_sample_flip(x2d, None, input_2d_flip=x2f, seed=8 + i)
+        e.record()
+        torch.cuda.synchronize()
+        parts.append(f"sampler(B={B},H={H},K={K}) {s.elapsed_time(e) / 3:.2f} ms max|diff vs first build| {diff:.3e}")
     print(f"{os.path.basename(os.environ['AB_LIB'])}: " + " | ".join(parts), flush=True)
 
 
@@ -92,6 +120,9 @@ if __name__ == "__main__":
         csrc = os.path.join(ROOT, "d3dp_b200", "csrc")
         libs = sys.argv[1:3] if len(sys.argv) >= 3 else ["libd3dp_b200.so", "ab_variant.so"]
         libs = [p if os.path.isabs(p) else os.path.join(csrc, p) for p in libs]
+        ref = os.path.join(os.environ.get("AB_TMP", "/tmp"), "ab_lib_sampler_ref.pt")
+        if os.path.exists(ref):
+            os.remove(ref)
         for lib in (libs[0], libs[1]) * int(os.environ.get("AB_VISITS", "2")):
             subprocess.run([sys.executable, os.path.abspath(__file__), "one"], env=dict(os.environ, AB_LIB=lib),
                            timeout=300)
