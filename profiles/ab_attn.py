@@ -1,4 +1,7 @@
-"""Same-box A/B of temporal-attention builds / knobs: parity against the fp32 torch restatement and CUDA-event timing
+"""Historical (round 1, session 2): produced r01b_ab_attn.log by comparing the build saved as ab_prev.so with the
+current one; the D3DP_ATTN_POLY knob it sets no longer exists.  Superseded by profiles/ab_lib.py.
+
+Same-box A/B of temporal-attention builds / knobs: parity against the fp32 torch restatement and CUDA-event timing
 at the bench shape (160 streams x 17 joints x 243).  Each configuration runs in its own process:
     python profiles/ab_attn.py                      # driver: loops over (library, D3DP_ATTN_POLY)
     AB_LIB=path python profiles/ab_attn.py one      # one configuration"""

@@ -1,4 +1,7 @@
-"""Same-box A/B of two builds of the cta_group::2 GEMMs at the bench shape (T = 660 960 rows): CUDA-event time of qkv
+"""Historical (round 1, session 2): produced r01b_ab_gemm.log (an earlier revision looped over the D3DP_GEMM_DEEP stage
+variants inside one process).  Superseded by profiles/ab_lib.py.
+
+Same-box A/B of two builds of the cta_group::2 GEMMs at the bench shape (T = 660 960 rows): CUDA-event time of qkv
 (N=1536) and fc1+GELU (N=1024) and a checksum of the outputs (builds must agree bit for bit).
     python profiles/ab_gemm.py                  # driver: ab_prev.so, libd3dp_b200.so, alternating, own processes
     AB_LIB=path python profiles/ab_gemm.py one"""
