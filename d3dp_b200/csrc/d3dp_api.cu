@@ -728,6 +728,10 @@ int d3dp_test_gemm(d3dp_handle* h, int32_t mode, const void* a16, const void* w1
                    float* x, const float* g_a, const float* b_a, float eps_a, const float* g_b, const float* b_b,
                    float eps_b, const float* tpos, int32_t F, int32_t M, int32_t N, int32_t K, void* stream) {
   if (!h || !a16 || !w16 || !bias) return fail(h, D3DP_E_INVALID, "test_gemm: bad argument");
+  // the kernels read parameters with 64/128-bit loads (the handle's own weight slots are cudaMalloc-aligned)
+  if ((reinterpret_cast<uintptr_t>(bias) & 15) || (reinterpret_cast<uintptr_t>(a16) & 15) ||
+      (reinterpret_cast<uintptr_t>(w16) & 15))
+    return fail(h, D3DP_E_INVALID, "test_gemm: a16, w16 and bias must be 16-byte aligned");
   int rc;
   if ((rc = ensure_attrs(h))) return rc;
   CUtensorMap tmA, tmB;
