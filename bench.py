@@ -19,6 +19,7 @@ on a bounded sample of the same workload.
 import argparse
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -28,18 +29,21 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-F_FRAMES, B_CLIPS, H_PER_GPU, K_STEPS = 243, 4, 20, 10
+F_FRAMES, B_CLIPS, H_PER_GPU, K_STEPS = 243, 4, 20, 10   # BASELINE config 3 (default); --config c2 overrides
 METRIC = "poses/sec (H=20,K=10,F=243)"
+CONFIG_NAME = "c3"
+CONFIGS = {"c3": (243, 4, 20, 10, "poses/sec (H=20,K=10,F=243)"),
+           "c2": (243, 1, 5, 5, "poses/sec (H=5,K=5,F=243)")}  # BASELINE config 2: single-GPU denoiser, B=1 assumed
 C, J = 512, 17
 
 
 def workload_config(world):
     F, B, H, K = F_FRAMES, B_CLIPS, H_PER_GPU, K_STEPS
-    return {"workload": f"c3: F={F} J=17 C=512 depth=8, B={B} clips, H={H}/GPU (H_total={H * world}), K={K}, "
+    return {"workload": f"{CONFIG_NAME}: F={F} J=17 C=512 depth=8, B={B} clips, H={H}/GPU (H_total={H * world}), K={K}, "
                         f"flip-TTA, Philox noise in-kernel, JPMA (J-Agg+P-Agg) included",
             "parallelism": f"hypothesis-sharded x{world}, one NCCL all-gather" if world > 1 else "single GPU",
             "l2": "activation working set 4.6 GB per step >> 126 MB L2 (no flush needed)",
-            "unit_definition": "pose = one output frame at H=20,K=10: B*F*(H_total/20) per step"}
+            "unit_definition": f"pose = one output frame at H={H},K={K}: B*F*(H_total/{H}) per step"}
 
 
 def f_tok(F):
@@ -179,7 +183,7 @@ def run_reference_arm(args, rank):
         return
     value, t, cores = cpu_reference_sample(args.steps, args.warmup)
     sample = (f"oracle port of D3DP.ddim_sample_flip on CPU, B=1 H=1 K=1 F=243 (2 MixSTE2 forwards) per step, "
-              f"{t:.2f} s/step; scaled by B*H*K linearity to H=20,K=10")
+              f"{t:.2f} s/step; scaled by B*H*K linearity to the config's H, K")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "poses/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
@@ -230,7 +234,7 @@ def kernel_rooflines(eng, T, n_streams, peaks):
             kw["ln_b"] = (ones, zeros, 1e-6)
         t = timeit(lambda: eng.test_gemm(mode, a, w, bias, F=eng.frames, **kw))
         fl = 2.0 * T * w.shape[0] * w.shape[1]
-        byt = KERNEL_MODEL[name][0] * T
+        byt = KERNEL_BYTES[name] * T
         res[name] = {"ms": t * 1e3, "tflops": fl / t / 1e12, "frac_tensor": fl / t / 1e12 / peaks["tflops"],
                      "gbs": byt / t / 1e9, "frac_hbm": byt / t / 1e9 / peaks["hbm_gbs"]}
     qkv = torch.cat([a512, a512, a512], dim=1).contiguous()
@@ -244,35 +248,60 @@ def kernel_rooflines(eng, T, n_streams, peaks):
     return res
 
 
-# algorithmic HBM bytes per token of each kernel and the resource that bounds it
-KERNEL_MODEL = {"gemm_qkv": (4096, "tensor"), "gemm_fc1_gelu": (3072, "tensor"), "gemm_proj_res_ln": (6144, "hbm"),
-                "gemm_fc2_res_ln2": (7168, "hbm"), "attn_temporal": (4096, "hbm"), "attn_spatial": (4096, "hbm")}
-# DRAM bytes per launch measured with ncu (dram__bytes_read.sum + dram__bytes_write.sum, T = 660 960; profiles/)
-NCU_TRAFFIC = {"gemm_qkv": 2.97e9, "gemm_fc1_gelu": 1.97e9, "gemm_proj_res_ln": 4.0e9, "gemm_fc2_res_ln2": 4.68e9,
-               "attn_temporal": 2.68e9, "attn_spatial": 2.68e9}
+# algorithmic HBM bytes per token of each kernel as the pipeline is cut today
+KERNEL_BYTES = {"gemm_qkv": 4096, "gemm_fc1_gelu": 3072, "gemm_proj_res_ln": 6144, "gemm_fc2_res_ln2": 7168,
+                "attn_temporal": 4096, "attn_spatial": 4096}
+# ncu evidence for the per-kernel DRAM traffic and tensor-pipe utilisation: parsed from the committed summary of the
+# `ncu --set full` capture of these kernels at T = 660 960 (profiles/ncu_summary.py output); refreshed whenever a
+# kernel changes (profiles/README.md).  Nothing is hard-coded here.
+NCU_SUMMARY = os.path.join("profiles", "r02_ncu_kernels_summary.txt")
+NCU_PATTERNS = {"gemm_qkv": "gemm_2sm_kernel<0", "gemm_fc1_gelu": "gemm_2sm_kernel<1",
+                "gemm_proj_res_ln": "gemm_ln_pair_kernel<2", "gemm_fc2_res_ln2": "gemm_ln_pair_kernel<3",
+                "attn_temporal": "attn_temporal_kernel", "attn_spatial": "attn_spatial_kernel"}
 
 
-def roofline_of(name, k, flops, T, peaks):
-    byt, bound = KERNEL_MODEL[name]
-    traffic = NCU_TRAFFIC[name] if T == 2 * B_CLIPS * H_PER_GPU * J * F_FRAMES else None
-    if bound == "hbm":
-        ach = byt * T / (k["ms"] * 1e-3) / 1e9
-        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "bytes_per_launch": byt * T,
-                "peak_source": peaks["source"] + ", copy bandwidth"}
+def ncu_evidence():
+    """{kernel: {"traffic": dram bytes per launch, "tensor_pipe_pct": ...}} from NCU_SUMMARY (last capture wins)."""
+    path = os.path.join(ROOT, NCU_SUMMARY)
+    out = {}
+    if not os.path.exists(path):
+        return out
+    for line in open(path):
+        for name, pat in NCU_PATTERNS.items():
+            if pat not in line:
+                continue
+            f = dict(re.findall(r"(\w+%?)=([0-9.eE+-]+)", line))
+            try:
+                out[name] = {"traffic": (float(f["dram_rd"]) + float(f["dram_wr"])) * 1e9,
+                             "tensor_pipe_pct": float(f["tensor%"]), "dram_pct": float(f["dram%"])}
+            except KeyError:
+                pass
+    return out
+
+
+def roofline_of(name, k, flops, T, peaks, ncu, full_size):
+    """the path is a dense contraction, the bound is the tensor pipe — `frac` is algorithmic FLOPs of the
+    dominant kernel / its CUDA-event time / the measured burst bf16 peak.  The HBM fraction of the pipeline as it is
+    cut today (activations round-trip between the five kernels of a block) is reported beside it."""
+    ev = ncu.get(name) if full_size else None
+    gbs = KERNEL_BYTES[name] * T / (k["ms"] * 1e-3) / 1e9
     return {"kernel": name, "bound": "tensor", "achieved": k["tflops"], "peak": peaks["tflops"], "unit": "TFLOP/s",
-            "frac": k["tflops"] / peaks["tflops"], "traffic": traffic, "flops_per_launch": flops,
-            "peak_source": peaks["source"] + ", burst bf16"}
+            "frac": k["tflops"] / peaks["tflops"], "flops_per_launch": flops,
+            "traffic": ev["traffic"] if ev else None,
+            "traffic_source": NCU_SUMMARY if ev else None,
+            "tensor_pipe_pct_ncu": ev["tensor_pipe_pct"] if ev else None,
+            "frac_hbm_as_cut": gbs / peaks["hbm_gbs"], "hbm_gbs_as_cut": gbs,
+            "bytes_per_launch_as_cut": KERNEL_BYTES[name] * T,
+            "peak_source": peaks["source"] + ", burst bf16 (cuBLAS 8192^3) / copy bandwidth"}
 
 
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from d3dp_b200 import D3DP
-    from d3dp_b200.synthetic import (H36M_JOINTS_LEFT as JL, H36M_JOINTS_RIGHT as JR, flip_2d, synthetic_camera,
-                                     synthetic_pose_estimator_state)
-    from d3dp_b200.distributed import gather_hypotheses
-    from tests.util import make_args  # tiny argparse-namespace helper
+    from d3dp_b200.synthetic import (H36M_JOINTS_LEFT as JL, H36M_JOINTS_RIGHT as JR, flip_2d, make_args,
+                                     synthetic_camera, synthetic_pose_estimator_state)
+    from d3dp_b200.distributed import gather_shards
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -291,32 +320,64 @@ def run_ours(args, rank, world, local_rank):
     traj_h, cam_h = synthetic_camera(B, F)
     traj_host, cam_host = traj_h.pin_memory(), cam_h.pin_memory()
     x2d, x2d_flip, traj, cam = x2d_host.to(dev), x2d_flip_host.to(dev), traj_host.to(dev), cam_host.to(dev)
+    out_host = [torch.empty(B, K, F, 17, 3).pin_memory() for _ in range(2)]  # J-Agg, P-Agg poses of a step
 
-    def step(i, from_host=False):
+    # Pipeline of one step: sampler on the compute stream; the path's one collective (all-gather of the hypothesis
+    # shards, NCCL's own stream) and the JPMA aggregation of step i on a side stream, under the sampler of step i+1 —
+    # no rank waits for another on the compute stream.  Everything is joined before the closing event.
+    main = torch.cuda.current_stream()
+    side = torch.cuda.Stream(device=dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    phases, keep = [], []
+
+    def step(i, from_host=False, record=False):
         if from_host:
             a, b = x2d_host.to(dev, non_blocking=True), x2d_flip_host.to(dev, non_blocking=True)
             tr, cm = traj_host.to(dev, non_blocking=True), cam_host.to(dev, non_blocking=True)
         else:
             a, b, tr, cm = x2d, x2d_flip, traj, cam
+        e0, e1, e2, e3 = (ev(), ev(), ev(), ev()) if record else (None,) * 4
+        if record:
+            e0.record(main)
         preds = model.ddim_sample_flip(a, None, input_2d_flip=b, seed=1000 + i, h_offset=rank * H, H_total=H_total)
-        preds = gather_hypotheses(preds, world)
-        jagg, idx, pagg = eng.jpma(preds, tr, cm, a)
-        if from_host:
-            return jagg.to("cpu", non_blocking=True), pagg.to("cpu", non_blocking=True)
-        return jagg, pagg
+        done = torch.cuda.Event(enable_timing=record)
+        done.record(main)
+        buf, work = gather_shards(preds, world, async_op=True)
+        with torch.cuda.stream(side):
+            side.wait_event(done)
+            if work is not None:
+                work.wait()                      # the side stream waits for NCCL; the compute stream does not
+            if record:
+                e1.record(side)
+            jagg, idx, pagg = eng.jpma(buf, tr, cm, a, shards=world)
+            if record:
+                e2.record(side)
+            if from_host:
+                out_host[0].copy_(jagg, non_blocking=True)
+                out_host[1].copy_(pagg, non_blocking=True)
+            if record:
+                e3.record(side)
+        for t in (buf, a, tr, cm):
+            t.record_stream(side)
+        keep.append((preds, buf, jagg, pagg))    # alive until the pipeline has drained
+        del keep[:-3]
+        if record:
+            phases.append((e0, done, e1, e2, e3))
+        return buf, jagg, pagg
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(n, from_host):
+    def timed(n, from_host, record=False):
         barrier()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
+        s, e = ev(), ev()
+        s.record(main)
         for i in range(n):
-            step(i, from_host)
-        e.record()
+            step(i, from_host, record)
+        main.wait_stream(side)                   # join the aggregation of the last steps
+        e.record(main)
         barrier()
         t = torch.tensor([s.elapsed_time(e) * 1e-3], device=dev, dtype=torch.float64)
         if world > 1:
@@ -325,24 +386,50 @@ def run_ours(args, rank, world, local_rank):
 
     for i in range(args.warmup):
         step(i)
+    # N > 1: every rank recomputes ANOTHER rank's hypothesis shard (Philox noise is keyed by the global hypothesis
+    # index) and compares it bit for bit with the slice the all-gather delivered
+    shard_check = None
+    if world > 1:
+        buf, _, _ = step(0)
+        other = (rank + 1) % world
+        mine = model.ddim_sample_flip(x2d, None, input_2d_flip=x2d_flip, seed=1000, h_offset=other * H, H_total=H_total)
+        torch.cuda.synchronize()
+        ok = torch.tensor([int(torch.equal(mine, buf[other]))], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        shard_check = "bit-equal" if ok.item() == 1 else "MISMATCH"
+        del mine
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
     w0 = time.time()
-    t_total = timed(args.steps, False)
+    t_total = timed(args.steps, False, record=True)
     w1 = time.time()
     clocks = sampler.stop(w0, w1) if sampler else None
     step(0, True)  # warm the host path
     t_e2e = timed(args.steps, True)
 
-    units = B * F * (H_total / 20.0) * args.steps
+    # per-phase device times of the timed steps: min / max over ranks of the per-rank mean
+    ph = torch.tensor([[a.elapsed_time(b) for a, b in ((p[0], p[1]), (p[1], p[2]), (p[2], p[3]))] for p in phases],
+                      device=dev, dtype=torch.float64).mean(0)
+    ph_min, ph_max = ph.clone(), ph.clone()
+    if world > 1:
+        dist.all_reduce(ph_min, op=dist.ReduceOp.MIN)
+        dist.all_reduce(ph_max, op=dist.ReduceOp.MAX)
+    phase_ms = {n: {"min": ph_min[i].item(), "max": ph_max[i].item()}
+                for i, n in enumerate(("sampler", "all_gather_wait", "jpma"))}
+    phase_ms["note"] = ("per-rank mean over the timed steps, min/max over ranks; all_gather_wait = sampler end -> "
+                        "gathered shards visible on the side stream (overlaps the next step's sampler)")
+
+    units = B * F * (H_total / float(H_PER_GPU)) * args.steps
     value, e2e_value = units / t_total, units / t_e2e
     if rank != 0:
         return
     flops = sampler_flops(B, H_total, K, F) * args.steps
     n_streams = 2 * B * H
     T = n_streams * J * F
+    full_size = (F, B, H) == (243, 4, 20)
+    ncu = ncu_evidence()
     kern = kernel_rooflines(eng, T, n_streams, peaks)
     # per-step launch counts of each kernel -> share of the step and the dominant one
     per_step = {"gemm_qkv": 16 * K, "gemm_fc1_gelu": 16 * K, "gemm_proj_res_ln": 16 * K,
@@ -350,17 +437,19 @@ def run_ours(args, rank, world, local_rank):
     for k_, v in kern.items():
         v["launches_per_step"] = per_step[k_]
         v["share_of_step"] = v["ms"] * per_step[k_] / (t_total / args.steps * 1e3)
+        if full_size and k_ in ncu:
+            v["ncu"] = ncu[k_]
     dom = max(kern, key=lambda k_: kern[k_]["share_of_step"])
     dom_flops = {"gemm_qkv": 2.0 * T * 1536 * 512, "gemm_fc1_gelu": 2.0 * T * 1024 * 512,
                  "gemm_proj_res_ln": 2.0 * T * 512 * 512, "gemm_fc2_res_ln2": 2.0 * T * 512 * 1024,
                  "attn_temporal": 4.0 * F * C * T, "attn_spatial": 4.0 * J * C * T}[dom]
-    launches_per_call = K * (3 + 16 * 5 + 1 + 1) + 1 + 1  # fill_t,time_mlp,embed + 16 blocks x 5 + head + ddim; philox, jpma
+    launches_per_call = 1 + K * (3 + 16 * 5 + 1 + 1) + 1  # init_img; per step fill_t,time_mlp,embed + 16x5 + head + ddim; jpma
     cpu_line = None
     if world == 1 and not args.no_cpu_baseline:
         v, t_s, cores = cpu_reference_sample(repeats=4, warmup=1)
         cpu_line = {"value": v, "unit": "poses/s", "cores": cores, "kind": "port",
-                    "sample": f"oracle port, B=1 H=1 K=1 F=243 flip (2 forwards), {t_s:.2f} s each x4, "
-                              f"scaled by B*H*K linearity to H=20,K=10"}
+                    "sample": f"oracle port, B=1 H=1 K=1 F={F} flip (2 forwards), {t_s:.2f} s each x4, "
+                              f"scaled by B*H*K linearity to H={H},K={K}"}
     h2d = (x2d_host.numel() + x2d_flip_host.numel() + traj_host.numel() + cam_host.numel()) * 4
     d2h = 2 * B * K * F * 17 * 3 * 4
     line = {
@@ -372,21 +461,34 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": t_e2e / args.steps * 1e3,
-                "api": "D3DP.ddim_sample_flip + Engine.jpma from pinned host tensors, aggregated poses copied back"},
+                "api": "D3DP.ddim_sample_flip + Engine.jpma from pinned host tensors, aggregated poses copied back "
+                       "into pinned host buffers"},
         "gpu_launches": launches_per_call * args.steps,
+        "launch_mode": "one CUDA graph per sampler call (%d kernel nodes) + 1 JPMA launch" % (launches_per_call - 1),
+        "phase_ms": phase_ms,
         "sampler_tflops": flops / t_total / 1e12 / world,
         "sampler_frac_of_sustained_peak": flops / t_total / 1e12 / world / peaks["tflops_sustained"],
-        "roofline": roofline_of(dom, kern[dom], dom_flops, T, peaks),
+        "roofline": roofline_of(dom, kern[dom], dom_flops, T, peaks, ncu, full_size),
+        "attn_temporal": {"tensor_pipe_pct": ncu.get("attn_temporal", {}).get("tensor_pipe_pct") if full_size else None,
+                          "source": NCU_SUMMARY, "tflops": kern["attn_temporal"]["tflops"],
+                          "frac_tensor": kern["attn_temporal"]["frac_tensor"]},
         "kernels": kern,
     }
+    if shard_check:
+        line["shard_check"] = shard_check
     if cpu_line:
         line["cpu_baseline"] = cpu_line
         try:
             v, t_s = gpu_eager_reference_sample(dev)
+            a100 = 4.0  # assumed B200 : A100 ratio of eager fp32 (non-TF32) PyTorch throughput on this model
             line["gpu_eager_baseline"] = {
-                "value": v, "unit": "poses/s", "kind": "port", "speedup": value / v,
-                "sample": f"oracle port of the reference's eager fp32 PyTorch path on this GPU (ATen, TF32 off), "
-                          f"B=1 H=20 K=1 F=243 flip, {t_s * 1e3:.0f} ms, scaled by B*K linearity"}
+                "value": v, "unit": "poses/s", "kind": "port",
+                "speedup": value / v,
+                "a100_scaling_factor_assumed": a100,
+                "speedup_vs_a100_equivalent": value / v * a100,
+                "sample": f"oracle port (same ATen ops as the reference; /root/reference itself is not present on the "
+                          f"GPU box) in eager fp32 on this GPU, TF32 off, B=1 H=20 K=1 F={F} flip, {t_s * 1e3:.0f} ms, "
+                          f"scaled by B*K linearity; A100-equivalent = this / {a100:g} (assumption, stated)"}
         except Exception as ex:  # never let the extra baseline break the bench line
             line["gpu_eager_baseline"] = {"error": str(ex)[:200]}
     print(json.dumps(line), file=_OUT, flush=True)
@@ -409,7 +511,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS),
+                    help="c3 = BASELINE config 3/4 (the metric's configuration, default); c2 = BASELINE config 2")
     args = ap.parse_args()
+    global F_FRAMES, B_CLIPS, H_PER_GPU, K_STEPS, METRIC, CONFIG_NAME
+    CONFIG_NAME = args.config
+    F_FRAMES, B_CLIPS, H_PER_GPU, K_STEPS, METRIC = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -6,12 +6,14 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libd3dp_b200.so")
+# D3DP_LIB: run against another BUILD of the same sources (profiles/ab_lib.py variants, sanitizer builds); the default
+# is the in-tree library.  Either way it is this C-ABI library or an exception — there is nothing else to fall back to.
+LIB_PATH = os.environ.get("D3DP_LIB") or os.path.join(_HERE, "csrc", "libd3dp_b200.so")
 
 # every symbol include/d3dp_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "d3dp_create", "d3dp_destroy", "d3dp_last_error", "d3dp_set_weight", "d3dp_weights_missing",
-    "d3dp_set_schedule", "d3dp_get_alphas_cumprod", "d3dp_time_list", "d3dp_workspace_bytes", "d3dp_denoise",
+    "d3dp_set_schedule", "d3dp_schedule_host", "d3dp_get_alphas_cumprod", "d3dp_time_list", "d3dp_workspace_bytes", "d3dp_denoise",
     "d3dp_ddim_sample", "d3dp_q_sample", "d3dp_jpma", "d3dp_jpma_gt", "d3dp_pmpjpe",
     "d3dp_philox_normal", "d3dp_test_gemm", "d3dp_test_attn",
     "d3dp_version",
@@ -52,7 +54,8 @@ def load():
     lib.d3dp_last_error.restype = C.c_char_p
     lib.d3dp_set_weight.argtypes = [vp, C.c_char_p, f32p, C.c_int64, vp]
     lib.d3dp_weights_missing.argtypes = [vp]
-    lib.d3dp_set_schedule.argtypes = [vp, f64p, f64p, f64p, f64p, f64p, C.c_int32]
+    lib.d3dp_set_schedule.argtypes = [vp, f64p, f64p, f64p, f64p, f64p, C.c_int32, vp]
+    lib.d3dp_schedule_host.argtypes = [C.c_int32, f64p]
     lib.d3dp_get_alphas_cumprod.argtypes = [vp, f64p, C.c_int32]
     lib.d3dp_time_list.argtypes = [C.c_int32, C.c_int32, i32p]
     lib.d3dp_workspace_bytes.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
@@ -61,9 +64,9 @@ def load():
                                      C.c_int32, C.c_int32, C.c_int32, vp, C.c_size_t, vp]
     lib.d3dp_q_sample.argtypes = [vp, f32p, f32p, i64p, f32p, C.c_int32, C.c_int64, C.c_int32, vp]
     lib.d3dp_jpma.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, i32p, f32p, f32p, C.c_int32, C.c_int32, C.c_int32,
-                              C.c_int32, C.c_int32, vp]
+                              C.c_int32, C.c_int32, C.c_int32, vp]
     lib.d3dp_jpma_gt.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, f32p, i32p, f32p, f32p, f32p, f32p, C.c_int32,
-                                 C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+                                 C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
     lib.d3dp_pmpjpe.argtypes = [vp, f32p, f32p, f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
     lib.d3dp_philox_normal.argtypes = [vp, f32p, C.c_int32, C.c_int32, C.c_int64, C.c_uint64, C.c_int32, C.c_int32,
                                        C.c_uint32, vp]

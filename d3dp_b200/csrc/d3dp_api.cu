@@ -43,6 +43,16 @@ struct BlockW {
 
 }  // namespace
 
+// One instantiated CUDA graph of the whole K-step sampler loop (852 kernel nodes at depth 8, K = 10).  Everything that
+// differs between two calls with the same key goes through the DynArgs block in the workspace, so the graph is
+// replayed as is; the key holds everything that is baked into kernel parameters.
+struct SamplerGraph {
+  int B, H, K, flip, h_offset, H_total;
+  void* ws;
+  std::vector<int32_t> times;
+  cudaGraphExec_t exec;
+};
+
 struct d3dp_handle {
   d3dp_config cfg;
   int device = 0;
@@ -55,6 +65,9 @@ struct d3dp_handle {
   double* d_sqrt_ac = nullptr;   // device copies for q_sample
   double* d_sqrt_1mac = nullptr;
   bool attrs_set = false;
+  bool use_graph = true;                 // D3DP_GRAPH=0 in the environment: launch the sampler kernel by kernel
+  cudaStream_t cap_stream = nullptr;     // private stream the sampler is captured on (the caller's may be the legacy one)
+  std::vector<SamplerGraph> graphs;      // small cache, oldest evicted
 };
 
 namespace {
@@ -132,9 +145,9 @@ void bind_block(d3dp_handle* h, const std::string& pre, BlockW& b) {
 
 const float* F32(d3dp_handle* h, const char* name) { return static_cast<const float*>(h->slots[name].dev); }
 
-// cosine schedule in float64 (reference: common/diffusionpose.py:42-52,75-78,95-103)
-void compute_schedule(d3dp_handle* h) {
-  const int T = h->cfg.num_timesteps;
+// cosine schedule in float64 (reference: common/diffusionpose.py:42-52,75-78): alphas_cumprod[T].  Pure host code
+// (exported as d3dp_schedule_host so that it can be pinned against the reference's buffer without a GPU).
+void cosine_alphas_cumprod(int T, double* ac) {
   const double s = 0.008;
   const double pi = 3.14159265358979323846;
   std::vector<double> acp(T + 1);
@@ -145,17 +158,25 @@ void compute_schedule(d3dp_handle* h) {
   }
   const double a0 = acp[0];
   for (int i = 0; i <= T; ++i) acp[i] = acp[i] / a0;
-  h->ac.resize(T);
-  h->sqrt_recip.resize(T);
-  h->sqrt_recipm1.resize(T);
-  h->sqrt_ac.resize(T);
-  h->sqrt_1mac.resize(T);
   double cum = 1.0;
   for (int t = 0; t < T; ++t) {
     double beta = 1.0 - (acp[t + 1] / acp[t]);
     beta = std::fmin(std::fmax(beta, 0.0), 0.999);
     cum *= (1.0 - beta);
-    h->ac[t] = cum;
+    ac[t] = cum;
+  }
+}
+
+void compute_schedule(d3dp_handle* h) {  // common/diffusionpose.py:95-103
+  const int T = h->cfg.num_timesteps;
+  h->ac.resize(T);
+  h->sqrt_recip.resize(T);
+  h->sqrt_recipm1.resize(T);
+  h->sqrt_ac.resize(T);
+  h->sqrt_1mac.resize(T);
+  cosine_alphas_cumprod(T, h->ac.data());
+  for (int t = 0; t < T; ++t) {
+    const double cum = h->ac[t];
     h->sqrt_recip[t] = std::sqrt(1.0 / cum);
     h->sqrt_recipm1[t] = std::sqrt(1.0 / cum - 1.0);
     h->sqrt_ac[t] = std::sqrt(cum);
@@ -163,12 +184,20 @@ void compute_schedule(d3dp_handle* h) {
   }
 }
 
-int upload_schedule(d3dp_handle* h) {
+void drop_graphs(d3dp_handle* h) {
+  for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
+}
+
+// device copies of the two buffers q_sample reads, on the caller's stream (ordered after kernels already queued
+// there; the source vectors live in the handle, and a pageable-source cudaMemcpyAsync stages them before returning)
+int upload_schedule(d3dp_handle* h, cudaStream_t st) {
   const size_t n = h->ac.size() * sizeof(double);
   if (!h->d_sqrt_ac) CK(cudaMalloc(&h->d_sqrt_ac, n));
   if (!h->d_sqrt_1mac) CK(cudaMalloc(&h->d_sqrt_1mac, n));
-  CK(cudaMemcpy(h->d_sqrt_ac, h->sqrt_ac.data(), n, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(h->d_sqrt_1mac, h->sqrt_1mac.data(), n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpyAsync(h->d_sqrt_ac, h->sqrt_ac.data(), n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_sqrt_1mac, h->sqrt_1mac.data(), n, cudaMemcpyHostToDevice, st));
+  drop_graphs(h);  // the DDIM coefficients are baked into the captured kernel parameters
   return D3DP_OK;
 }
 
@@ -295,6 +324,7 @@ struct Workspace {
   float* tau;     // [B, 512]
   float* img;     // [B,H,F,17,3]
   long long* t;   // [B]
+  DynArgs* dyn;   // per-call arguments of the sampler graph
   size_t bytes;
 };
 
@@ -316,6 +346,7 @@ Workspace carve(const d3dp_handle* h, void* base, int B, int H, int n_streams) {
   w.tau = reinterpret_cast<float*>(take(static_cast<size_t>(B) * 512 * 4));
   w.img = reinterpret_cast<float*>(take(static_cast<size_t>(B) * H * h->cfg.frames * kJ * 3 * 4));
   w.t = reinterpret_cast<long long*>(take(static_cast<size_t>(B) * 8));
+  w.dyn = reinterpret_cast<DynArgs*>(take(sizeof(DynArgs)));
   w.bytes = off;
   return w;
 }
@@ -327,8 +358,9 @@ __global__ void fill_t_kernel(long long* t, int B, long long v) {
 
 // One MixSTE2 forward over n_streams streams (reference: common/mixste.py:278-298).  `img` is [B,H,F,17,3];
 // clamp_hi > 0 applies the sampler's clamp(+-1.1 scale)/scale on the fly (common/diffusionpose.py:136-137,148-149).
-int run_denoiser(d3dp_handle* h, const Workspace& w, const float* x2d, const float* x2d_flip, const float* img,
-                 const long long* t_dev, int B, int H, int n_streams, float clamp_hi, cudaStream_t st) {
+int run_denoiser(d3dp_handle* h, const Workspace& w, const DynArgs* dyn, const float* x2d, const float* x2d_flip,
+                 const float* img, const long long* t_dev, int B, int H, int n_streams, float clamp_hi,
+                 cudaStream_t st) {
   int rc;
   if ((rc = ensure_attrs(h))) return rc;
   const int F = h->cfg.frames, depth = h->cfg.depth;
@@ -339,7 +371,7 @@ int run_denoiser(d3dp_handle* h, const Workspace& w, const float* x2d, const flo
   CK(cudaGetLastError());
 
   EmbedParams ep;
-  ep.x2d = x2d; ep.x2d_flip = x2d_flip; ep.img = img;
+  ep.dyn = dyn; ep.x2d = x2d; ep.x2d_flip = x2d_flip; ep.img = img;
   ep.w_e = F32(h, "Spatial_patch_to_embedding.weight");
   ep.b_e = F32(h, "Spatial_patch_to_embedding.bias");
   ep.spos = F32(h, "Spatial_pos_embed");
@@ -424,15 +456,57 @@ int run_denoiser(d3dp_handle* h, const Workspace& w, const float* x2d, const flo
   return D3DP_OK;
 }
 
-int check_ready(d3dp_handle* h) {
-  if (d3dp_weights_missing(h) != 0) return fail(h, D3DP_E_WEIGHTS, "weights incomplete: call d3dp_set_weight for every tensor");
-  return D3DP_OK;
-}
-
 int grid_for(long long n, int num_sms) {
   long long b = (n + 255) / 256;
   const long long cap = static_cast<long long>(num_sms) * 8;
   return static_cast<int>(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+// The K-step DDIM loop (reference: common/diffusionpose.py:215-256), launched on `st` — directly, or into a stream
+// capture.  Caller-owned pointers and the seed are read from w.dyn by the kernels, never baked in here.
+int sampler_body(d3dp_handle* h, const Workspace& w, int B, int H, int K, int flip, int n_streams,
+                 const std::vector<int32_t>& times, int h_offset, int H_total, cudaStream_t st) {
+  int rc;
+  const int F = h->cfg.frames;
+  const long long per_bh = static_cast<long long>(F) * kJ * 3;
+  const long long n_img = static_cast<long long>(B) * H * per_bh;
+  // img ~ N(0, I)  (common/diffusionpose.py:225): injected, or Philox draw 0
+  init_img_kernel<<<grid_for(n_img, h->num_sms), 256, 0, st>>>(w.img, w.dyn, B, H, per_bh, h_offset, H_total);
+  CK(cudaGetLastError());
+  const float scale = h->cfg.scale;
+  for (int k = 0; k < K; ++k) {
+    const int t = times[k], t_next = times[k + 1];
+    fill_t_kernel<<<(B + 127) / 128, 128, 0, st>>>(w.t, B, static_cast<long long>(t));
+    CK(cudaGetLastError());
+    if ((rc = run_denoiser(h, w, w.dyn, nullptr, nullptr, w.img, w.t, B, H, n_streams, 1.1f * scale, st))) return rc;
+    DdimParams dp{};
+    dp.den = w.den; dp.img = w.img; dp.dyn = w.dyn;
+    dp.B = B; dp.H = H; dp.K = K; dp.F = F; dp.k = k;
+    dp.flip = flip; dp.last = t_next < 0 ? 1 : 0;
+    dp.scale = scale;
+    dp.out_scale = h->cfg.output_scale;
+    dp.sqrt_recip_ac = h->sqrt_recip[t];
+    dp.sqrt_recipm1_ac = h->sqrt_recipm1[t];
+    if (t_next >= 0) {
+      // eta = 1 DDIM coefficients in float64 (common/diffusionpose.py:244-248)
+      const double a = h->ac[t], an = h->ac[t_next];
+      const double sigma = 1.0 * std::sqrt((1 - a / an) * (1 - an) / (1 - a));
+      const double c = std::sqrt(1 - an - sigma * sigma);
+      dp.sigma = static_cast<float>(sigma);
+      dp.c = static_cast<float>(c);
+      dp.sqrt_ac_next = static_cast<float>(std::sqrt(an));
+    }
+    dp.h_offset = h_offset; dp.H_total = H_total;
+    for (int j = 0; j < kJ; ++j) dp.perm[j] = h->cfg.flip_perm[j];
+    ddim_step_kernel<<<grid_for(n_img, h->num_sms), 256, 0, st>>>(dp);
+    CK(cudaGetLastError());
+  }
+  return D3DP_OK;
+}
+
+int check_ready(d3dp_handle* h) {
+  if (d3dp_weights_missing(h) != 0) return fail(h, D3DP_E_WEIGHTS, "weights incomplete: call d3dp_set_weight for every tensor");
+  return D3DP_OK;
 }
 
 }  // namespace
@@ -499,8 +573,10 @@ int d3dp_create(const d3dp_config* cfg, d3dp_handle** out) {
       return D3DP_E_CUDA;
     }
   }
+  const char* genv = std::getenv("D3DP_GRAPH");
+  h->use_graph = !(genv && genv[0] == '0');
   compute_schedule(h);
-  if (upload_schedule(h) != D3DP_OK) {
+  if (upload_schedule(h, nullptr) != D3DP_OK) {
     d3dp_destroy(h);
     return D3DP_E_CUDA;
   }
@@ -514,6 +590,8 @@ void d3dp_destroy(d3dp_handle* h) {
     if (kv.second.dev) cudaFree(kv.second.dev);
   if (h->d_sqrt_ac) cudaFree(h->d_sqrt_ac);
   if (h->d_sqrt_1mac) cudaFree(h->d_sqrt_1mac);
+  drop_graphs(h);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   delete h;
 }
 
@@ -549,15 +627,21 @@ int d3dp_weights_missing(const d3dp_handle* h) {
   return n;
 }
 
+int d3dp_schedule_host(int32_t num_timesteps, double* alphas_cumprod_out) {
+  if (num_timesteps < 1 || !alphas_cumprod_out) return D3DP_E_INVALID;
+  cosine_alphas_cumprod(num_timesteps, alphas_cumprod_out);
+  return D3DP_OK;
+}
+
 int d3dp_set_schedule(d3dp_handle* h, const double* ac, const double* sr, const double* srm1, const double* sac,
-                      const double* s1mac, int32_t n) {
+                      const double* s1mac, int32_t n, void* stream) {
   if (!h || !ac || !sr || !srm1 || !sac || !s1mac || n != h->cfg.num_timesteps) return D3DP_E_INVALID;
   h->ac.assign(ac, ac + n);
   h->sqrt_recip.assign(sr, sr + n);
   h->sqrt_recipm1.assign(srm1, srm1 + n);
   h->sqrt_ac.assign(sac, sac + n);
   h->sqrt_1mac.assign(s1mac, s1mac + n);
-  return upload_schedule(h);
+  return upload_schedule(h, static_cast<cudaStream_t>(stream));
 }
 
 int d3dp_get_alphas_cumprod(const d3dp_handle* h, double* out, int32_t n) {
@@ -596,7 +680,8 @@ int d3dp_denoise(d3dp_handle* h, const float* x2d, const float* x_t, const int64
   Workspace w = carve(h, workspace, B, H, B * H);
   if (w.bytes > workspace_bytes) return fail(h, D3DP_E_WORKSPACE, "denoise: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if ((rc = run_denoiser(h, w, x2d, nullptr, x_t, reinterpret_cast<const long long*>(t), B, H, B * H, 0.f, st))) return rc;
+  if ((rc = run_denoiser(h, w, nullptr, x2d, nullptr, x_t, reinterpret_cast<const long long*>(t), B, H, B * H, 0.f, st)))
+    return rc;
   CK(cudaMemcpyAsync(out, w.den, static_cast<size_t>(B) * H * h->cfg.frames * kJ * 3 * 4, cudaMemcpyDeviceToDevice, st));
   return D3DP_OK;
 }
@@ -607,17 +692,16 @@ int d3dp_ddim_sample(d3dp_handle* h, const float* x2d, const float* x2d_flip, co
                      size_t workspace_bytes, void* stream) {
   if (!h || !x2d || !preds || !workspace || B < 1 || H < 1 || K < 1 || K > h->cfg.num_timesteps)
     return fail(h, D3DP_E_INVALID, "ddim_sample: bad argument");
-  if (H_total < h_offset + H) return fail(h, D3DP_E_INVALID, "ddim_sample: h_offset + H exceeds H_total");
+  if (h_offset < 0 || H_total < h_offset + H)
+    return fail(h, D3DP_E_INVALID, "ddim_sample: need 0 <= h_offset and h_offset + H <= H_total");
   int rc;
   if ((rc = check_ready(h))) return rc;
+  if ((rc = ensure_attrs(h))) return rc;
   const int flip = x2d_flip ? 1 : 0;
   const int n_streams = B * H * (flip ? 2 : 1);
   Workspace w = carve(h, workspace, B, H, n_streams);
   if (w.bytes > workspace_bytes) return fail(h, D3DP_E_WORKSPACE, "ddim_sample: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int F = h->cfg.frames;
-  const long long per_bh = static_cast<long long>(F) * kJ * 3;
-  const long long n_img = static_cast<long long>(B) * H * per_bh;
 
   std::vector<int32_t> times(K + 1);
   if (timesteps_host) {
@@ -629,42 +713,45 @@ int d3dp_ddim_sample(d3dp_handle* h, const float* x2d, const float* x2d_flip, co
     if (times[k] < 0 || times[k] >= h->cfg.num_timesteps || times[k + 1] >= times[k] || (k + 1 < K && times[k + 1] < 0))
       return fail(h, D3DP_E_INVALID, "ddim_sample: bad timestep list");
 
-  // img ~ N(0, I)  (common/diffusionpose.py:225)
-  if (noise_init) {
-    CK(cudaMemcpyAsync(w.img, noise_init, static_cast<size_t>(n_img) * 4, cudaMemcpyDeviceToDevice, st));
-  } else {
-    philox_fill_kernel<<<grid_for(n_img, h->num_sms), 256, 0, st>>>(w.img, B, H, per_bh, seed, h_offset, H_total, 0u);
-    CK(cudaGetLastError());
-  }
-  const float scale = h->cfg.scale;
-  for (int k = 0; k < K; ++k) {
-    const int t = times[k], t_next = times[k + 1];
-    fill_t_kernel<<<(B + 127) / 128, 128, 0, st>>>(w.t, B, static_cast<long long>(t));
-    CK(cudaGetLastError());
-    if ((rc = run_denoiser(h, w, x2d, x2d_flip, w.img, w.t, B, H, n_streams, 1.1f * scale, st))) return rc;
-    DdimParams dp{};
-    dp.den = w.den; dp.img = w.img; dp.preds = preds;
-    dp.noise = (noise_steps && t_next >= 0) ? noise_steps + static_cast<size_t>(k) * n_img : nullptr;
-    dp.B = B; dp.H = H; dp.K = K; dp.F = F; dp.k = k;
-    dp.flip = flip; dp.last = t_next < 0 ? 1 : 0;
-    dp.scale = scale;
-    dp.out_scale = h->cfg.output_scale;
-    dp.sqrt_recip_ac = h->sqrt_recip[t];
-    dp.sqrt_recipm1_ac = h->sqrt_recipm1[t];
-    if (t_next >= 0) {
-      // eta = 1 DDIM coefficients in float64 (common/diffusionpose.py:244-248)
-      const double a = h->ac[t], an = h->ac[t_next];
-      const double sigma = 1.0 * std::sqrt((1 - a / an) * (1 - an) / (1 - a));
-      const double c = std::sqrt(1 - an - sigma * sigma);
-      dp.sigma = static_cast<float>(sigma);
-      dp.c = static_cast<float>(c);
-      dp.sqrt_ac_next = static_cast<float>(std::sqrt(an));
+  // everything that changes from call to call goes through the DynArgs block (one small H2D copy, staged before return)
+  const DynArgs dyn{x2d, x2d_flip, noise_init, noise_steps, preds, static_cast<unsigned long long>(seed)};
+  CK(cudaMemcpyAsync(w.dyn, &dyn, sizeof(DynArgs), cudaMemcpyHostToDevice, st));
+
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (st) cudaStreamIsCapturing(st, &cap);
+  if (!h->use_graph || cap != cudaStreamCaptureStatusNone)
+    return sampler_body(h, w, B, H, K, flip, n_streams, times, h_offset, H_total, st);
+
+  // replay (or first build) the captured loop: reference common/diffusionpose.py:229-254
+  SamplerGraph* g = nullptr;
+  for (auto& c : h->graphs)
+    if (c.B == B && c.H == H && c.K == K && c.flip == flip && c.h_offset == h_offset && c.H_total == H_total &&
+        c.ws == workspace && c.times == times)
+      g = &c;
+  if (!g) {
+    if (!h->cap_stream) CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    rc = sampler_body(h, w, B, H, K, flip, n_streams, times, h_offset, H_total, h->cap_stream);
+    const cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      return rc;
     }
-    dp.seed = seed; dp.h_offset = h_offset; dp.H_total = H_total;
-    for (int j = 0; j < kJ; ++j) dp.perm[j] = h->cfg.flip_perm[j];
-    ddim_step_kernel<<<grid_for(n_img, h->num_sms), 256, 0, st>>>(dp);
-    CK(cudaGetLastError());
+    if (ce != cudaSuccess) return fail(h, D3DP_E_CUDA, std::string("sampler graph capture failed: ") + cudaGetErrorString(ce));
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) return fail(h, D3DP_E_CUDA, std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ie));
+    if (h->graphs.size() >= 8) {
+      cudaGraphExecDestroy(h->graphs.front().exec);
+      h->graphs.erase(h->graphs.begin());
+    }
+    h->graphs.push_back(SamplerGraph{B, H, K, flip, h_offset, H_total, workspace, times, exec});
+    g = &h->graphs.back();
   }
+  CK(cudaGraphLaunch(g->exec, st));
   return D3DP_OK;
 }
 
@@ -682,14 +769,17 @@ int d3dp_q_sample(d3dp_handle* h, const float* x0, const float* noise, const int
 
 int d3dp_jpma_gt(d3dp_handle* h, const float* preds, const float* traj, const float* cam, const float* x2d,
                  const float* gt, float* jagg_pose, int32_t* jagg_idx, float* pagg_pose, float* e2d_min, float* e3d,
-                 float* jbest_pose, int32_t B, int32_t K, int32_t H, int32_t root_joint, int32_t linear, void* stream) {
+                 float* jbest_pose, int32_t B, int32_t K, int32_t H, int32_t root_joint, int32_t linear,
+                 int32_t hyp_shards, void* stream) {
   if (!h || !preds || !traj || !cam || !x2d || !jagg_pose || !jagg_idx || !pagg_pose || B < 1 || K < 1 || H < 1)
     return fail(h, D3DP_E_INVALID, "jpma: bad argument");
+  if (hyp_shards < 1 || H % hyp_shards != 0 || (gt && hyp_shards != 1))
+    return fail(h, D3DP_E_INVALID, "jpma: hyp_shards must divide H (and be 1 with ground truth)");
   JpmaParams p;
   p.pred = preds; p.traj = traj; p.cam = cam; p.x2d = x2d;
   p.jagg_pose = jagg_pose; p.jagg_idx = jagg_idx; p.pagg_pose = pagg_pose; p.e2d_min = e2d_min;
   p.gt = gt; p.e3d = gt ? e3d : nullptr; p.jbest_pose = gt ? jbest_pose : nullptr;
-  p.B = B; p.K = K; p.H = H; p.F = h->cfg.frames; p.root = root_joint; p.linear = linear;
+  p.B = B; p.K = K; p.H = H; p.F = h->cfg.frames; p.root = root_joint; p.linear = linear; p.shards = hyp_shards;
   const long long n = static_cast<long long>(B) * K * p.F * kJ;
   jpma_kernel<<<grid_for(n, h->num_sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   CK(cudaGetLastError());
@@ -710,9 +800,9 @@ int d3dp_pmpjpe(d3dp_handle* h, const float* preds, const float* gt, float* perr
 
 int d3dp_jpma(d3dp_handle* h, const float* preds, const float* traj, const float* cam, const float* x2d,
               float* jagg_pose, int32_t* jagg_idx, float* pagg_pose, float* e2d_min, int32_t B, int32_t K, int32_t H,
-              int32_t root_joint, int32_t linear, void* stream) {
+              int32_t root_joint, int32_t linear, int32_t hyp_shards, void* stream) {
   return d3dp_jpma_gt(h, preds, traj, cam, x2d, nullptr, jagg_pose, jagg_idx, pagg_pose, e2d_min, nullptr, nullptr, B, K,
-                      H, root_joint, linear, stream);
+                      H, root_joint, linear, hyp_shards, stream);
 }
 
 int d3dp_philox_normal(d3dp_handle* h, float* out, int32_t B, int32_t H, int64_t per_bh, uint64_t seed,

@@ -89,7 +89,20 @@ __global__ void __launch_bounds__(512) time_mlp_kernel(const long long* __restri
 // Streams: s in [0, B*H) read (x2d, clamp(img)/scale); with flip TTA streams [B*H, 2*B*H) read
 // (x2d_flip, flip(clamp(img)/scale)) where flip negates coordinate 0 and swaps left/right joints
 // (reference: common/diffusionpose.py:148-153).  Token order out: row = (s*17 + j)*F + f.  One warp per token.
+// Per-call arguments of the sampler that live in DEVICE memory (one 64-byte block in the workspace, refreshed with a
+// single H2D copy before every call): the K-step loop is a CUDA graph replayed across calls, so nothing that changes
+// from call to call (caller-owned pointers, the noise seed) may be baked into its kernel parameters.
+struct DynArgs {
+  const float* x2d;          // [B,F,17,2]
+  const float* x2d_flip;     // [B,F,17,2] (flip TTA) or null
+  const float* noise_init;   // [B,H,F,17,3] or null -> Philox draw 0
+  const float* noise_steps;  // [K-1,B,H,F,17,3] or null -> Philox draw k+1
+  float* preds;              // [B,K,H,F,17,3]
+  unsigned long long seed;
+};
+
 struct EmbedParams {
+  const DynArgs* dyn;     // sampler: x2d / x2d_flip are read from here (null: the two fields below are used)
   const float* x2d;       // [B,F,17,2]
   const float* x2d_flip;  // [B,F,17,2] or null
   const float* img;       // [B,H,F,17,3]
@@ -121,6 +134,8 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int BH = p.B * p.H;
   const long long T = static_cast<long long>(p.n_streams) * kJ * p.F;
+  const float* x2d_plain = p.dyn ? p.dyn->x2d : p.x2d;
+  const float* x2d_flip = p.dyn ? p.dyn->x2d_flip : p.x2d_flip;
   const int c0 = lane * 16;  // this lane's channels [c0, c0 + 16)
   float we[16][5], be[16], lg[16], lb[16];
 #pragma unroll
@@ -141,7 +156,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
     const int b = bh / p.H;
     float in[5];
     {
-      const float* src2 = (flip ? p.x2d_flip : p.x2d) + ((static_cast<size_t>(b) * p.F + f) * kJ + j) * 2;
+      const float* src2 = (flip ? x2d_flip : x2d_plain) + ((static_cast<size_t>(b) * p.F + f) * kJ + j) * 2;
       in[0] = src2[0];
       in[1] = src2[1];
       const int js = flip ? p.perm[j] : j;
@@ -202,6 +217,8 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int BH = p.B * p.H;
   const long long T = static_cast<long long>(p.n_streams) * kJ * p.F;
+  const float* x2d_plain = p.dyn ? p.dyn->x2d : p.x2d;
+  const float* x2d_flip = p.dyn ? p.dyn->x2d_flip : p.x2d_flip;
   // lane owns channels c = i*32 + lane: its slice of W_e, b_e and the norm1 affine stays in registers for all tokens
   float we[16][5], be[16], lg[16], lb[16];
 #pragma unroll
@@ -223,7 +240,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
     const int b = bh / p.H;
     float in[5];
     {
-      const float* src2 = (flip ? p.x2d_flip : p.x2d) + ((static_cast<size_t>(b) * p.F + f) * kJ + j) * 2;
+      const float* src2 = (flip ? x2d_flip : x2d_plain) + ((static_cast<size_t>(b) * p.F + f) * kJ + j) * 2;
       in[0] = src2[0];
       in[1] = src2[1];
       const int js = flip ? p.perm[j] : j;
@@ -335,8 +352,7 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ x, 
 struct DdimParams {
   const float* den;     // [n_streams, F, 17, 3]
   float* img;           // [B,H,F,17,3] state, updated in place
-  float* preds;         // [B,K,H,F,17,3]
-  const float* noise;   // injected N(0,1) for this step [B,H,F,17,3] or null -> Philox
+  const DynArgs* dyn;   // preds [B,K,H,F,17,3], injected noise_steps (or null -> Philox) and the seed
   int B, H, K, F, k;
   int flip;             // 1: TTA streams present
   int last;             // 1: img = x0
@@ -344,7 +360,6 @@ struct DdimParams {
   float out_scale;      // preds are stored as x0 * out_scale (1000 for the 3DHP / mm variant)
   double sqrt_recip_ac, sqrt_recipm1_ac;
   float sqrt_ac_next, c, sigma;
-  unsigned long long seed;
   int h_offset, H_total;  // global hypothesis index = h_offset + h (Philox addressing)
   int perm[kJ];
 };
@@ -353,6 +368,9 @@ __global__ void __launch_bounds__(256) ddim_step_kernel(const DdimParams p) {
   const long long per_bh = static_cast<long long>(p.F) * kJ * 3;
   const long long n = static_cast<long long>(p.B) * p.H * per_bh;
   const long long BH = static_cast<long long>(p.B) * p.H;
+  float* preds = p.dyn->preds;
+  const float* noise = (p.dyn->noise_steps && !p.last) ? p.dyn->noise_steps + static_cast<size_t>(p.k) * n : nullptr;
+  const unsigned long long seed = p.dyn->seed;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % 3);
@@ -369,7 +387,7 @@ __global__ void __launch_bounds__(256) ddim_step_kernel(const DdimParams p) {
     float x0 = __fmul_rn(pred, p.scale);
     x0 = fminf(fmaxf(x0, -1.1f * p.scale), 1.1f * p.scale);
     const int b = static_cast<int>(bh / p.H), h = static_cast<int>(bh % p.H);
-    p.preds[(((static_cast<long long>(b) * p.K + p.k) * p.H + h) * per_bh) + (i - bh * per_bh)] =
+    preds[(((static_cast<long long>(b) * p.K + p.k) * p.H + h) * per_bh) + (i - bh * per_bh)] =
         p.out_scale == 1.0f ? x0 : __fmul_rn(x0, p.out_scale);
     if (p.last) {
       p.img[i] = x0;
@@ -378,12 +396,12 @@ __global__ void __launch_bounds__(256) ddim_step_kernel(const DdimParams p) {
       const float eps = static_cast<float>((p.sqrt_recip_ac * static_cast<double>(xi) - static_cast<double>(x0)) /
                                            p.sqrt_recipm1_ac);
       float z;
-      if (p.noise) {
-        z = p.noise[i];
+      if (noise) {
+        z = noise[i];
       } else {
         const unsigned long long ge =
             (static_cast<unsigned long long>(b) * p.H_total + (p.h_offset + h)) * per_bh + (i - bh * per_bh);
-        z = philox_normal(p.seed, static_cast<uint32_t>(p.k + 1), ge);
+        z = philox_normal(seed, static_cast<uint32_t>(p.k + 1), ge);
       }
       p.img[i] = __fadd_rn(__fadd_rn(__fmul_rn(x0, p.sqrt_ac_next), __fmul_rn(p.c, eps)), __fmul_rn(p.sigma, z));
     }
@@ -401,6 +419,26 @@ __global__ void philox_fill_kernel(float* __restrict__ img, int B, int H, long l
     const unsigned long long ge =
         (static_cast<unsigned long long>(b) * H_total + (h_offset + h)) * per_bh + (i - bh * per_bh);
     img[i] = philox_normal(seed, draw, ge);
+  }
+}
+
+// sampler form: injected noise_init if the call gave one, else Philox draw 0 with the call's seed (both via DynArgs)
+__global__ void init_img_kernel(float* __restrict__ img, const DynArgs* __restrict__ dyn, int B, int H,
+                                long long per_bh, int h_offset, int H_total) {
+  const long long n = static_cast<long long>(B) * H * per_bh;
+  const float* src = dyn->noise_init;
+  const unsigned long long seed = dyn->seed;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (src) {
+      img[i] = src[i];
+    } else {
+      const long long bh = i / per_bh;
+      const int b = static_cast<int>(bh / H), h = static_cast<int>(bh % H);
+      const unsigned long long ge =
+          (static_cast<unsigned long long>(b) * H_total + (h_offset + h)) * per_bh + (i - bh * per_bh);
+      img[i] = philox_normal(seed, 0u, ge);
+    }
   }
 }
 
@@ -445,6 +483,8 @@ struct JpmaParams {
   float* jbest_pose;   // [B,K,F,17,3] or null: argmin_h e3d
   int B, K, H, F, root;
   int linear;          // 1: project_to_2d_linear (focal + principal point only)
+  int shards;          // pred is [shards, B, K, H/shards, F,17,3] (the rank-major layout an NCCL all-gather of the
+                       // per-rank [B,K,h,F,17,3] tensors produces); 1 = the plain [B,K,H,F,17,3] layout
 };
 
 __global__ void __launch_bounds__(256) jpma_kernel(const JpmaParams p) {
@@ -468,9 +508,11 @@ __global__ void __launch_bounds__(256) jpma_kernel(const JpmaParams p) {
       gx = gp[0]; gy = gp[1]; gz = gp[2];
     }
     float sx = 0.f, sy = 0.f, sz = 0.f;
+    const int h_loc = p.H / p.shards;
     for (int h = 0; h < p.H; ++h) {
+      const int r = h / h_loc, hl = h - r * h_loc;  // global hypothesis h = shard r, local index hl
       const float* q =
-          p.pred + ((((static_cast<size_t>(b) * p.K + k) * p.H + h) * p.F + f) * kJ + j) * 3;
+          p.pred + (((((static_cast<size_t>(r) * p.B + b) * p.K + k) * h_loc + hl) * p.F + f) * kJ + j) * 3;
       float px = q[0], py = q[1], pz = q[2];
       if (j == p.root) px = py = pz = 0.f;
       sx = __fadd_rn(sx, px);
@@ -496,10 +538,12 @@ __global__ void __launch_bounds__(256) jpma_kernel(const JpmaParams p) {
         pv = __fadd_rn(__fmul_rn(cm[1], Y3), cm[3]);
       }
       const float du = __fsub_rn(pu, u), dv = __fsub_rn(pv, v);
-      const float e = __fsqrt_rn(__fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)));
+      // torch.norm(dim=-1) accumulates acc = fma(x, x, acc) in element order (checked bit for bit against ATen's CPU
+      // kernel on 110 160 values, tests/test_oracle_cpu.py): e = sqrt(fma(dv, dv, du*du))
+      const float e = __fsqrt_rn(__fmaf_rn(dv, dv, __fmul_rn(du, du)));
       if (p.gt) {
         const float ax = __fsub_rn(px, gx), ay = __fsub_rn(py, gy), az = __fsub_rn(pz, gz);
-        const float e3 = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az)));
+        const float e3 = __fsqrt_rn(__fmaf_rn(az, az, __fmaf_rn(ay, ay, __fmul_rn(ax, ax))));
         if (p.e3d) p.e3d[(((static_cast<size_t>(b) * p.K + k) * p.H + h) * p.F + f) * kJ + j] = e3;
         if (e3 < best3) { best3 = e3; jx = px; jy = py; jz = pz; }
       }

@@ -106,9 +106,12 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+#ifndef LNX_ABLATE
+#define LNX_ABLATE 0  // diagnostic builds: 1 = mainloop only (no epilogue work), 2 = epilogue only (no operands / MMA)
+#endif
   if (warp == 0) {
     // ------------------------------------------------------------------ operand TMA producer
-    if (lane == 0) {
+    if (lane == 0 && LNX_ABLATE != 2) {
       int s = 0;
       uint32_t ph = 0;
       for (int tile = cluster_id; tile < tiles_m; tile += num_clusters) {
@@ -125,7 +128,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && LNX_ABLATE != 2) {
       constexpr uint32_t idesc = make_idesc_f16(128, 256, 0, 0);
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
@@ -151,7 +154,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------------ residual TMA loader (x tile, 32-col chunks)
-    if (lane == 0) {
+    if (lane == 0 && LNX_ABLATE != 1) {
       int slot = 0;
       uint32_t ph = 0;
       for (int tile = cluster_id; tile < tiles_m; tile += num_clusters) {
@@ -246,7 +249,18 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool valid = grow < p.M;
       const bool write_a = p.out16 != nullptr;
       const int f = valid ? (grow % p.F) : 0;
+#if LNX_ABLATE == 1
       mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aph ^= 1; }
+      continue;
+#endif
+#if LNX_ABLATE != 2
+      mbar_wait(&tfull_bar[as], aph);
+#endif
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256 + lcol0;
 

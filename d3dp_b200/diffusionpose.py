@@ -77,15 +77,29 @@ class D3DP(nn.Module):
             joints_left=self.joints_left, joints_right=self.joints_right, scale=args.scale,
             output_scale=self.OUTPUT_SCALE)
         self._sched_fp = {}
+        self._sched = {"master": self, "epoch": 0}  # shared with nn.DataParallel replicas (shallow copies)
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._bump_schedule())
+
+    def _bump_schedule(self):
+        self._sched["epoch"] += 1
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if "_sched" in self.__dict__:
+            self._bump_schedule()
+        return out
 
     # ------------------------------------------------------------------ engine
     def _engine(self):
         eng = self.pose_estimator.engine()
-        bufs = (self.alphas_cumprod, self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod,
-                self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod)
-        fp = tuple((b.data_ptr(), b._version) for b in bufs)
-        if self._sched_fp.get(id(eng)) != fp:  # buffers may have been replaced by load_state_dict
-            eng.set_schedule(*bufs)
+        names = ("alphas_cumprod", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+                 "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod")
+        # keyed on the module that owns the buffers (DataParallel replicas get fresh broadcast copies every forward):
+        # its epoch (load_state_dict / .to() / .cuda()) and the buffers' version counters (in-place edits)
+        master = self._sched["master"]
+        fp = (self._sched["epoch"],) + tuple(getattr(master, n)._version for n in names)
+        if self._sched_fp.get(id(eng)) != fp:
+            eng.set_schedule(*(getattr(self, n) for n in names))  # 5 x 1000 doubles, once per change
             self._sched_fp[id(eng)] = fp
         return eng
 

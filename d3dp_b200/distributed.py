@@ -19,17 +19,35 @@ def shard_range(H_total, world, rank):
     return h_offset, h_local
 
 
+def gather_shards(preds, world, group=None, async_op=False):
+    """The path's one collective: all-gather the per-rank [B,K,h,F,17,3] shards (equal h on every rank) into the
+    rank-major buffer [world,B,K,h,F,17,3] exactly as `all_gather_into_tensor` lays it down — no re-layout copy.
+    `Engine.jpma(..., shards=world)` aggregates straight from this layout (global hypothesis r*h + hl = shard r,
+    local hl); `shards_to_reference_layout` materialises the reference's [B,K,H,F,17,3] when a caller wants it.
+    async_op=True returns (buffer, work): the collective runs on NCCL's own stream, so the caller can queue the next
+    sampler call on the compute stream and `work.wait()` on a side stream before the aggregation."""
+    if world == 1:
+        return (preds[None], None) if async_op else preds[None]
+    preds = preds.contiguous()
+    out = torch.empty((world,) + tuple(preds.shape), dtype=preds.dtype, device=preds.device)
+    # concatenation form along dim 0 (accepted by every backend); `flat` is a view of `out`
+    flat = out.view((world * preds.shape[0],) + tuple(preds.shape[1:]))
+    work = dist.all_gather_into_tensor(flat, preds, group=group, async_op=async_op)
+    return (out, work) if async_op else out
+
+
+def shards_to_reference_layout(shards):
+    """[world,B,K,h,F,17,3] -> the reference's [B,K,world*h,F,17,3] (one permute copy)."""
+    W, B, K, h = shards.shape[:4]
+    return shards.permute(1, 2, 0, 3, 4, 5, 6).reshape(B, K, W * h, *shards.shape[4:])
+
+
 def gather_hypotheses(preds, world, group=None):
     """all-gather [B,K,h,F,17,3] from every rank into [B,K,h*world,F,17,3] (equal h on all ranks), ordered by rank =
     ordered by global hypothesis index.  One collective: dist.all_gather_into_tensor."""
     if world == 1:
         return preds
-    preds = preds.contiguous()
-    B, K, h = preds.shape[:3]
-    out = torch.empty((world * B,) + tuple(preds.shape[1:]), dtype=preds.dtype, device=preds.device)
-    dist.all_gather_into_tensor(out, preds, group=group)  # rank-major concatenation along dim 0
-    out = out.reshape((world,) + tuple(preds.shape))
-    return out.permute(1, 2, 0, 3, 4, 5, 6).reshape(B, K, world * h, *preds.shape[3:])
+    return shards_to_reference_layout(gather_shards(preds, world, group))
 
 
 def gather_hypotheses_uneven(preds, H_total, world, rank, group=None):

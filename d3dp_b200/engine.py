@@ -69,8 +69,9 @@ class Engine:
     def set_schedule(self, alphas_cumprod, sqrt_recip, sqrt_recipm1, sqrt_ac, sqrt_1mac):
         arrs = [a.detach().to("cpu", torch.float64).contiguous()
                 for a in (alphas_cumprod, sqrt_recip, sqrt_recipm1, sqrt_ac, sqrt_1mac)]
-        check(self.handle, self.lib.d3dp_set_schedule(self.handle, *[ptr(a) for a in arrs], arrs[0].numel()),
-              "d3dp_set_schedule")
+        with torch.cuda.device(self.device):
+            check(self.handle, self.lib.d3dp_set_schedule(self.handle, *[ptr(a) for a in arrs], arrs[0].numel(),
+                                                          _stream()), "d3dp_set_schedule")
 
     def alphas_cumprod(self):
         out = torch.empty(self.num_timesteps, dtype=torch.float64)
@@ -131,9 +132,15 @@ class Engine:
                                                       x0.numel() // B, int(clamp), _stream()), "d3dp_q_sample")
         return out
 
-    def jpma(self, preds, traj, cam, x2d, root_joint=0, linear=False, return_e2d=False):
+    def jpma(self, preds, traj, cam, x2d, root_joint=0, linear=False, return_e2d=False, shards=1):
+        """J-Agg / P-Agg.  shards=1: preds [B,K,H,F,17,3]; shards=W: preds [W,B,K,H/W,F,17,3], the rank-major output of
+        the all-gather of the per-rank hypothesis shards (distributed.gather_shards)."""
         preds, traj, cam, x2d = self._f32(preds), self._f32(traj), self._f32(cam), self._f32(x2d)
-        B, K, H = preds.shape[0], preds.shape[1], preds.shape[2]
+        if shards == 1:
+            B, K, H = preds.shape[0], preds.shape[1], preds.shape[2]
+        else:
+            assert preds.dim() == 7 and preds.shape[0] == shards
+            B, K, H = preds.shape[1], preds.shape[2], preds.shape[3] * shards
         traj = traj.reshape(B, self.frames, 3)
         if cam.dim() == 1:
             cam = cam[None].expand(B, 9).contiguous()
@@ -144,7 +151,7 @@ class Engine:
         with torch.cuda.device(self.device):
             check(self.handle, self.lib.d3dp_jpma(self.handle, ptr(preds), ptr(traj), ptr(cam), ptr(x2d), ptr(jagg),
                                                   ptr(idx), ptr(pagg), ptr(e2d), B, K, H, int(root_joint), int(linear),
-                                                  _stream()), "d3dp_jpma")
+                                                  int(shards), _stream()), "d3dp_jpma")
         return (jagg, idx, pagg, e2d) if return_e2d else (jagg, idx, pagg)
 
     def jpma_gt(self, preds, traj, cam, x2d, gt, root_joint=0, linear=False):
@@ -160,7 +167,7 @@ class Engine:
         with torch.cuda.device(self.device):
             check(self.handle, self.lib.d3dp_jpma_gt(
                 self.handle, ptr(preds), ptr(traj), ptr(cam), ptr(x2d), ptr(gt), ptr(jagg), ptr(idx), ptr(pagg),
-                ptr(e2d), ptr(e3d), ptr(jbest), B, K, H, int(root_joint), int(linear), _stream()), "d3dp_jpma_gt")
+                ptr(e2d), ptr(e3d), ptr(jbest), B, K, H, int(root_joint), int(linear), 1, _stream()), "d3dp_jpma_gt")
         return {"jagg_pose": jagg, "jagg_idx": idx, "pagg_pose": pagg, "e2d_min": e2d, "e3d": e3d, "jbest_pose": jbest}
 
     def pmpjpe(self, preds, gt, root_joint=0):

@@ -65,8 +65,27 @@ class MixSTE2(nn.Module):
         self.Temporal_norm = norm_layer(C)
         self.head = nn.Sequential(nn.LayerNorm(C), nn.Linear(C, 3))
         self._engines = {}  # device index -> (Engine, weights fingerprint); shared by DataParallel replicas
+        # nn.DataParallel replicas are shallow copies of this module whose parameters are fresh broadcast tensors on
+        # every forward (version 0, recycled addresses): they find the module that owns the real parameters through
+        # this shared cell and key their packed copies on ITS state.
+        self._shared = {"master": self, "epoch": 0}
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.refresh_weights())
 
     # ------------------------------------------------------------------ engine management
+    def refresh_weights(self):
+        """Force the packed fp16 copy inside the engine(s) to be rebuilt on the next forward.  Called automatically
+        after load_state_dict (also through a parent / nn.DataParallel) and after .to()/.cuda()/.float() (`_apply`);
+        optimizer steps and other in-place ops are seen through the parameters' version counters.  Writes that bypass
+        autograd's version counter (`p.data.copy_(...)`, `p.data.mul_(...)`, e.g. a hand-written EMA) are invisible to
+        any cheap check: call this method after them."""
+        self._shared["epoch"] += 1
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if "_shared" in self.__dict__:
+            self.refresh_weights()
+        return out
+
     def _named_weights(self):
         """{reference state_dict key: tensor} for this module tree.  Also works inside nn.DataParallel replicas, whose
         parameters are plain attributes recorded in `_former_parameters` (state_dict() / parameters() are empty there)."""
@@ -80,7 +99,15 @@ class MixSTE2(nn.Module):
         return out
 
     def _fingerprint(self, weights):
-        return tuple((p.data_ptr(), p._version) for p in weights.values())
+        """Identity of the weights the engine on this device was packed from.  Always the MASTER module's epoch and
+        parameter versions (a replica's own tensors say nothing: new every forward); plus, for the master itself,
+        the storage addresses (a parameter re-bound with `p.data = new_tensor` keeps its version)."""
+        master = self._shared["master"]
+        mw = weights if master is self else master._named_weights()
+        fp = (self._shared["epoch"],) + tuple(p._version for p in mw.values())
+        if master is self:
+            fp += tuple(p.data_ptr() for p in mw.values())
+        return fp
 
     def engine(self):
         """The per-device Engine with this module's current weights uploaded (re-packed when any parameter changed)."""
@@ -102,11 +129,16 @@ class MixSTE2(nn.Module):
         return ent[0]
 
     # ------------------------------------------------------------------ reference surface
-    @torch.no_grad()
     def forward(self, x_2d, x_3d, t):
         """common/mixste.py:278-298.  eval: x_2d [b,f,17,2], x_3d [b,h,f,17,3], t [b] -> [b,h,f,17,3];
-        train layout (is_train=True): x_3d [b,f,17,3] -> [b,f,17,3] (forward only, no stochastic depth)."""
-        eng = self.engine()
-        if self.is_train:
-            return eng.denoise(x_2d, x_3d[:, None], t)[:, 0]
-        return eng.denoise(x_2d, x_3d, t)
+        train layout (is_train=True): x_3d [b,f,17,3] -> [b,f,17,3].  Forward only: the kernels keep nothing for a
+        backward pass, so a training-mode call under autograd is refused instead of returning a detached tensor."""
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "d3dp_b200.MixSTE2 is forward-only (sm_100a inference kernels, no backward): call it under "
+                "torch.no_grad() / in eval() mode, or train with the reference implementation")
+        with torch.no_grad():
+            eng = self.engine()
+            if self.is_train:
+                return eng.denoise(x_2d, x_3d[:, None], t)[:, 0]
+            return eng.denoise(x_2d, x_3d, t)

@@ -6,6 +6,7 @@ shipping 140 MB of weights.  Shapes/keys are the reference's `pose_estimator.*` 
 (common/mixste.py:142-210; 208 tensors).
 """
 import math
+import types
 import zlib
 
 import torch
@@ -14,6 +15,12 @@ H36M_JOINTS_LEFT = [4, 5, 6, 11, 12, 13]
 H36M_JOINTS_RIGHT = [1, 2, 3, 14, 15, 16]
 # Human3.6M camera 0 intrinsics, normalised (common/h36m_dataset.py:20-29,216-231): f(2) c(2) k(3) p(2)
 H36M_CAM0 = [2.2901, 2.2876, 0.0251, 0.0289, -0.2071, 0.2478, -0.0031, -0.00098, -0.00142]
+
+
+def make_args(frames, scale=1.0, depth=8, flip=True):
+    """The fields D3DP.__init__ reads from the reference's argparse namespace (common/arguments.py:49-50,58,101-102,112)."""
+    return types.SimpleNamespace(number_of_frames=frames, test_time_augmentation=flip, timestep=1000, scale=scale,
+                                 cs=512, dep=depth)
 
 
 def pose_estimator_shapes(frames, depth=8, C=512):

@@ -68,7 +68,11 @@ int d3dp_weights_missing(const d3dp_handle* h);
  * `sqrt_one_minus_alphas_cumprod`; common/diffusionpose.py:92-103) — load_state_dict may overwrite them. */
 int d3dp_set_schedule(d3dp_handle* h, const double* alphas_cumprod_host, const double* sqrt_recip_host,
                       const double* sqrt_recipm1_host, const double* sqrt_ac_host, const double* sqrt_1mac_host,
-                      int32_t n);
+                      int32_t n, void* stream);
+/* The schedule d3dp_create computes when d3dp_set_schedule is never called: alphas_cumprod[num_timesteps] of
+ * cosine_beta_schedule (common/diffusionpose.py:42-52,75-78) in float64.  Host-only (no handle, no GPU), so the C
+ * restatement can be pinned against the reference's registered buffer (tests/test_host_cpu.py). */
+int d3dp_schedule_host(int32_t num_timesteps, double* alphas_cumprod_out_host);
 /* Copy the handle's own float64 alphas_cumprod (host) — used to pin the C schedule against the reference's. */
 int d3dp_get_alphas_cumprod(const d3dp_handle* h, double* out_host, int32_t n);
 
@@ -89,8 +93,12 @@ int d3dp_denoise(d3dp_handle* h, const float* x2d, const float* x_t, const int64
  *   noise_init  [B,H,F,17,3]      or NULL -> Philox(seed, draw 0)
  *   noise_steps [K-1,B,H,F,17,3]  or NULL -> Philox(seed, draw k+1)
  * Philox noise is addressed by the global hypothesis index h_offset + h inside H_total, so a hypothesis gets the
- * same noise on whatever GPU it is computed.  timesteps_host: K+1 descending ints ending in -1, or NULL to use
- * d3dp_time_list. */
+ * same noise on whatever GPU it is computed (0 <= h_offset, h_offset + H <= H_total).  timesteps_host: K+1
+ * descending ints ending in -1, or NULL to use d3dp_time_list.
+ * The loop of common/diffusionpose.py:229-254 is captured once per (B, H, K, flip, h_offset, H_total, timesteps,
+ * workspace) into a CUDA graph and replayed on `stream`; caller-owned pointers and the seed reach the kernels through
+ * a small device-side argument block, so they may change freely between calls.  (Environment D3DP_GRAPH=0 at
+ * d3dp_create, or a `stream` that is itself being captured: plain kernel-by-kernel launches.) */
 int d3dp_ddim_sample(d3dp_handle* h, const float* x2d, const float* x2d_flip, const float* noise_init,
                      const float* noise_steps, uint64_t seed, int32_t h_offset, int32_t H_total,
                      const int32_t* timesteps_host, float* preds, int32_t B, int32_t H, int32_t K, void* workspace,
@@ -107,10 +115,15 @@ int d3dp_q_sample(d3dp_handle* h, const float* x0, const float* noise, const int
  * reprojection error (J-Agg) and the hypothesis mean (P-Agg).
  *   preds [B,K,H,F,17,3]  traj [B,F,3]  cam [B,9]  x2d [B,F,17,2]
  *   jagg_pose, pagg_pose [B,K,F,17,3]   jagg_idx [B,K,F,17] int32   e2d_min [B,K,F,17] or NULL
- * linear != 0 selects project_to_2d_linear (common/camera.py:62-80). */
+ * linear != 0 selects project_to_2d_linear (common/camera.py:62-80).
+ * hyp_shards = 1: preds is the reference's [B,K,H,F,17,3].  hyp_shards = W > 1: preds is [W,B,K,H/W,F,17,3], the
+ * rank-major buffer one NCCL all-gather of the per-rank [B,K,H/W,F,17,3] shards produces (global hypothesis
+ * r*(H/W)+hl = shard r, local hl), so the multi-GPU path needs no re-layout copy before the aggregation.
+ * The 2-D error and the per-joint argmin are bit-equal to the reference's torch.norm / torch.min on the CPU
+ * (first index wins ties). */
 int d3dp_jpma(d3dp_handle* h, const float* preds, const float* traj, const float* cam, const float* x2d,
               float* jagg_pose, int32_t* jagg_idx, float* pagg_pose, float* e2d_min, int32_t B, int32_t K, int32_t H,
-              int32_t root_joint, int32_t linear, void* stream);
+              int32_t root_joint, int32_t linear, int32_t hyp_shards, void* stream);
 
 /* JPMA with ground truth (evaluation only; main.py:715-718 metrics and main_3dhp.py:785-799 pose export):
  * everything d3dp_jpma produces plus, against gt[B,F,17,3] (root joint zeroed by the caller like main.py:683),
@@ -119,7 +132,8 @@ int d3dp_jpma(d3dp_handle* h, const float* preds, const float* traj, const float
  * either may be NULL. */
 int d3dp_jpma_gt(d3dp_handle* h, const float* preds, const float* traj, const float* cam, const float* x2d,
                  const float* gt, float* jagg_pose, int32_t* jagg_idx, float* pagg_pose, float* e2d_min, float* e3d,
-                 float* jbest_pose, int32_t B, int32_t K, int32_t H, int32_t root_joint, int32_t linear, void* stream);
+                 float* jbest_pose, int32_t B, int32_t K, int32_t H, int32_t root_joint, int32_t linear,
+                 int32_t hyp_shards, void* stream);
 
 /* Protocol-2 (Procrustes-aligned) per-joint errors (evaluation only; common/loss.py:190-395 p_mpjpe_diffusion_all_min,
  * p_mpjpe_diffusion, p_mpjpe_diffusion_reproj — there a device->numpy round trip with a batched LAPACK SVD):

@@ -88,7 +88,7 @@ def one():
         from d3dp_b200 import D3DP
         from d3dp_b200.synthetic import (H36M_JOINTS_LEFT as JL, H36M_JOINTS_RIGHT as JR, flip_2d,
                                          synthetic_pose_estimator_state)
-        from tests.util import make_args
+        from d3dp_b200.synthetic import make_args
         F, B, H, K = 243, 2, 10, 2
         model = D3DP(make_args(F), JL, JR, is_train=False, num_proposals=H, sampling_timesteps=K)
         model.pose_estimator.load_state_dict(synthetic_pose_estimator_state(F, seed=0), strict=True)

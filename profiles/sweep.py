@@ -12,7 +12,7 @@ from bench import f_tok, measured_peaks  # noqa: E402
 from d3dp_b200 import D3DP  # noqa: E402
 from d3dp_b200.synthetic import (H36M_JOINTS_LEFT as JL, H36M_JOINTS_RIGHT as JR, flip_2d,  # noqa: E402
                                  synthetic_pose_estimator_state)
-from tests.util import make_args  # noqa: E402
+from d3dp_b200.synthetic import make_args  # noqa: E402
 
 
 def main():

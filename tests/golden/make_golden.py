@@ -22,13 +22,19 @@ CASES = [
     ("f27_scale2",    27, 1, 2, 3, True, 2.0, 8, 1),
     ("f9_depth2",     9,  2, 2, 2, True, 1.0, 2, 2),
     ("f243_flip",     243, 1, 2, 2, True, 1.0, 8, 0),
+    # round 2: the benchmarked depth of the DDIM loop, and BASELINE config 2 exactly as stated
+    ("f243_k10",      243, 1, 1, 10, True, 1.0, 8, 0),  # K=10 (the headline setting's step count), one chain
+    ("f243_c2",       243, 1, 5, 5, True, 1.0, 8, 0),   # BASELINE config 2: F=243, B=1, H=5, K=5
 ]
 
 
 def main():
     assert rh.available()
     torch.set_num_threads(os.cpu_count())
+    only = set(sys.argv[1:])
     for name, F, B, H, K, flip, scale, depth, wseed in CASES:
+        if only and name not in only:
+            continue
         sd = synthetic_pose_estimator_state(F, depth=depth, seed=wseed)
         x2d, x2d_flip, n0, ns = synthetic_inputs(B, H, K, F)
         model = rh.build_reference_model(F, H, K, sd, JL, JR, scale=scale, depth=depth, flip=flip)

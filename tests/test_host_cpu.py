@@ -21,6 +21,30 @@ def test_library_exports_every_symbol_in_header():
     assert b"sm_100a" in lib.d3dp_version()
 
 
+def test_c_schedule_matches_reference_buffer():
+    """The schedule d3dp_create computes for a C-ABI user who never calls d3dp_set_schedule (d3dp_schedule_host, plain
+    C doubles with libm's cos) against the buffer the reference registers (common/diffusionpose.py:42-52,92-95; the
+    oracle's schedule_buffers is bit-equal to it, oracle/validate_against_reference.py).  torch.cos is a vectorised
+    SLEEF kernel, libm's is scalar: both are <= 1 ulp routines, and the cumulative product of 1000 factors may drift
+    by a few ulp — the bound asserted here is 1e-13 relative (float32 coefficients need 6e-8); the Python surface
+    always uploads torch's own buffers (D3DP._engine -> d3dp_set_schedule), which are the reference's bit for bit."""
+    import ctypes as C
+
+    import numpy as np
+
+    from d3dp_b200 import _lib
+    from oracle import d3dp_oracle as orc
+    lib = _lib.load()
+    out = np.empty(1000, dtype=np.float64)
+    assert lib.d3dp_schedule_host(1000, out.ctypes.data_as(C.c_void_p)) == 0
+    ref = orc.schedule_buffers(1000)["alphas_cumprod"].numpy()
+    rel = np.abs(out - ref) / ref
+    print(f"\n[schedule] C vs reference alphas_cumprod: bit-equal {int((out == ref).sum())}/1000, "
+          f"max rel diff {rel.max():.2e}")
+    assert rel.max() < 1e-13
+    assert lib.d3dp_schedule_host(0, out.ctypes.data_as(C.c_void_p)) != 0
+
+
 def test_engine_fails_loudly_without_gpu():
     if torch.cuda.is_available():
         pytest.skip("GPU present")

@@ -110,3 +110,22 @@ def test_jpma_oracle_properties():
     # H = 1: J-Agg == P-Agg == the hypothesis
     j1, _, p1, _ = orc.jpma(preds[:, :, :1], traj, cam, x2d)
     assert torch.equal(j1, p1)
+
+
+def test_torch_norm_association_is_the_fma_chain_the_jpma_kernel_uses():
+    """The JPMA kernel takes its per-joint argmin over e2d = sqrt(fma(dv, dv, du*du)) and e3d = sqrt(fma(dz, dz,
+    fma(dy, dy, dx*dx))) (d3dp_b200/csrc/elementwise.cuh).  That is exactly how ATen's CPU torch.norm(dim=-1)
+    accumulates over a short last axis, which is what the reference's loss functions call (common/loss.py:54-76):
+    checked here bit for bit with float64 emulation of the fused multiply-adds, so index-exact argmin parity on the
+    GPU (tests/test_aux_gpu.py::test_jpma_matches_oracle) rests on a checked identity, not on luck."""
+    g = torch.Generator().manual_seed(5)
+    d = torch.randn(50000, 3, generator=g) * torch.logspace(-3, 1, 50000)[:, None]
+    f32 = np.float32
+    a = d.numpy().astype(np.float64)
+
+    def rn(x):
+        return x.astype(f32).astype(np.float64)
+    e2 = np.sqrt(rn(a[:, 1] * a[:, 1] + rn(a[:, 0] * a[:, 0])).astype(f32))
+    e3 = np.sqrt(rn(a[:, 2] * a[:, 2] + rn(a[:, 1] * a[:, 1] + rn(a[:, 0] * a[:, 0]))).astype(f32))
+    assert np.array_equal(torch.norm(d[:, :2], dim=-1).numpy().view(np.uint32), e2.view(np.uint32))
+    assert np.array_equal(torch.norm(d, dim=-1).numpy().view(np.uint32), e3.view(np.uint32))

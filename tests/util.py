@@ -1,23 +1,19 @@
 """Shared helpers for the tests (test infrastructure)."""
 import os
-import types
 
 import torch
 
-from d3dp_b200.synthetic import (H36M_JOINTS_LEFT as JL, H36M_JOINTS_RIGHT as JR, synthetic_inputs,
-                                 synthetic_pose_estimator_state)
+from d3dp_b200.synthetic import (H36M_JOINTS_LEFT as JL, H36M_JOINTS_RIGHT as JR, make_args,  # noqa: F401
+                                 synthetic_inputs, synthetic_pose_estimator_state)
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_CASES = ["f27_flip", "f27_noflip_k1", "f27_scale2", "f9_depth2", "f243_flip"]
+GOLDEN_CASES = ["f27_flip", "f27_noflip_k1", "f27_scale2", "f9_depth2", "f243_flip",
+                "f243_k10",   # K = 10, the benchmarked depth of the DDIM loop (one chain)
+                "f243_c2"]    # BASELINE config 2 exactly: F=243, B=1, H=5, K=5
 
 
 def load_golden(name):
     return torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=True)
-
-
-def make_args(frames, scale=1.0, depth=8, flip=True):
-    return types.SimpleNamespace(number_of_frames=frames, test_time_augmentation=flip, timestep=1000, scale=scale,
-                                 cs=512, dep=depth)
 
 
 def case_inputs(case):
