@@ -59,7 +59,7 @@ def load():
     lib.d3dp_get_alphas_cumprod.argtypes = [vp, f64p, C.c_int32]
     lib.d3dp_time_list.argtypes = [C.c_int32, C.c_int32, i32p]
     lib.d3dp_workspace_bytes.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
-    lib.d3dp_denoise.argtypes = [vp, f32p, f32p, i64p, f32p, C.c_int32, C.c_int32, vp, C.c_size_t, vp]
+    lib.d3dp_denoise.argtypes = [vp, f32p, f32p, i64p, f32p, f32p, C.c_int32, C.c_int32, vp, C.c_size_t, vp]
     lib.d3dp_ddim_sample.argtypes = [vp, f32p, f32p, f32p, f32p, C.c_uint64, C.c_int32, C.c_int32, i32p, f32p,
                                      C.c_int32, C.c_int32, C.c_int32, vp, C.c_size_t, vp]
     lib.d3dp_q_sample.argtypes = [vp, f32p, f32p, i64p, f32p, C.c_int32, C.c_int64, C.c_int32, vp]

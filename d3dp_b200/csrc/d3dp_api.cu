@@ -217,10 +217,15 @@ constexpr int kSmemGemmQkv = Gemm2SmSmem<6, 1, false>::TOTAL;
 auto* const k_gemm_fc1 = gemm_2sm_kernel<EPI_BIAS_GELU_F16, 4, 2, true>;
 constexpr int kSmemGemmFc1 = Gemm2SmSmem<4, 2, true>::TOTAL;
 static_assert(kSmemGemmQkv <= 232448 && kSmemGemmFc1 <= 232448, "exceeds the 227 KB of shared memory per CTA");
-constexpr int kLnStages = 2, kLnRing = 2;
+#ifndef D3DP_LN_STAGES
+#define D3DP_LN_STAGES 2
+#define D3DP_LN_RING 2
+#endif
+constexpr int kLnStages = D3DP_LN_STAGES, kLnRing = D3DP_LN_RING;
 auto* const k_gemm_proj = gemm_ln_pair_kernel<EPI_RES_LN, kLnStages, kLnRing>;
 auto* const k_gemm_fc2 = gemm_ln_pair_kernel<EPI_RES_LN2, kLnStages, kLnRing>;
 constexpr int kSmemN512 = LnPairSmem<kLnStages, kLnRing>::TOTAL;
+static_assert(kSmemN512 <= 232448, "LN pair kernel exceeds the 227 KB of shared memory per CTA");
 
 int ensure_attrs(d3dp_handle* h) {
   if (h->attrs_set) return D3DP_OK;
@@ -360,7 +365,7 @@ __global__ void fill_t_kernel(long long* t, int B, long long v) {
 // clamp_hi > 0 applies the sampler's clamp(+-1.1 scale)/scale on the fly (common/diffusionpose.py:136-137,148-149).
 int run_denoiser(d3dp_handle* h, const Workspace& w, const DynArgs* dyn, const float* x2d, const float* x2d_flip,
                  const float* img, const long long* t_dev, int B, int H, int n_streams, float clamp_hi,
-                 cudaStream_t st) {
+                 cudaStream_t st, const float* drop_scale = nullptr) {
   int rc;
   if ((rc = ensure_attrs(h))) return rc;
   const int F = h->cfg.frames, depth = h->cfg.depth;
@@ -400,9 +405,18 @@ int run_denoiser(d3dp_handle* h, const Workspace& w, const DynArgs* dyn, const f
   const float* ln_t_b = F32(h, "Temporal_norm.bias");
   const float* tpos = F32(h, "Temporal_pos_embed");
 
+  // DropPath scales (training forward): per block d [S attn | S mlp] n_streams*F each, [T attn | T mlp] n_streams*17 each
+  const size_t ds_S = static_cast<size_t>(n_streams) * F, ds_T = static_cast<size_t>(n_streams) * kJ;
   for (int d = 0; d < depth; ++d) {
     for (int which = 0; which < 2; ++which) {  // 0 = spatial block, 1 = temporal block
       const BlockW& bw = which == 0 ? h->sblk[d] : h->tblk[d];
+      const float* ds_attn = nullptr;
+      const float* ds_mlp = nullptr;
+      if (drop_scale) {
+        const float* base = drop_scale + d * (2 * ds_S + 2 * ds_T) + (which == 0 ? 0 : 2 * ds_S);
+        ds_attn = base;
+        ds_mlp = base + (which == 0 ? ds_S : ds_T);
+      }
       GemmParams p{};
       p.F = F;
       // qkv = Linear(norm1(x))  (a16 already holds norm1(x))
@@ -422,6 +436,7 @@ int run_denoiser(d3dp_handle* h, const Workspace& w, const DynArgs* dyn, const f
       p.ln_a_g = static_cast<const float*>(bw.n2w->dev);
       p.ln_a_b = static_cast<const float*>(bw.n2b->dev);
       p.ln_a_eps = 1e-6f;
+      p.row_scale = ds_attn; p.rs_mode = which == 0 ? 1 : 2;
       if ((rc = launch_gemm(h, EPI_RES_LN, tm_o, bw.projw->tmap, p, st))) return rc;
       // hidden = gelu(fc1(a16))
       p = GemmParams{};
@@ -438,6 +453,7 @@ int run_denoiser(d3dp_handle* h, const Workspace& w, const DynArgs* dyn, const f
       p.ln_a_b = which == 0 ? ln_s_b : ln_t_b;
       p.ln_a_eps = 1e-6f;
       p.tpos = (which == 0 && d == 0) ? tpos : nullptr;
+      p.row_scale = ds_mlp; p.rs_mode = which == 0 ? 1 : 2;
       const BlockW* next = which == 0 ? &h->tblk[d] : (d + 1 < depth ? &h->sblk[d + 1] : nullptr);
       if (next) {
         p.ln_b_g = static_cast<const float*>(next->n1w->dev);
@@ -672,15 +688,16 @@ int d3dp_workspace_bytes(const d3dp_handle* h, int32_t B, int32_t H, int32_t fli
   return D3DP_OK;
 }
 
-int d3dp_denoise(d3dp_handle* h, const float* x2d, const float* x_t, const int64_t* t, float* out, int32_t B,
-                 int32_t H, void* workspace, size_t workspace_bytes, void* stream) {
+int d3dp_denoise(d3dp_handle* h, const float* x2d, const float* x_t, const int64_t* t, const float* drop_scale,
+                 float* out, int32_t B, int32_t H, void* workspace, size_t workspace_bytes, void* stream) {
   if (!h || !x2d || !x_t || !t || !out || !workspace || B < 1 || H < 1) return fail(h, D3DP_E_INVALID, "denoise: bad argument");
   int rc;
   if ((rc = check_ready(h))) return rc;
   Workspace w = carve(h, workspace, B, H, B * H);
   if (w.bytes > workspace_bytes) return fail(h, D3DP_E_WORKSPACE, "denoise: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if ((rc = run_denoiser(h, w, nullptr, x2d, nullptr, x_t, reinterpret_cast<const long long*>(t), B, H, B * H, 0.f, st)))
+  if ((rc = run_denoiser(h, w, nullptr, x2d, nullptr, x_t, reinterpret_cast<const long long*>(t), B, H, B * H, 0.f, st,
+                         drop_scale)))
     return rc;
   CK(cudaMemcpyAsync(out, w.den, static_cast<size_t>(B) * H * h->cfg.frames * kJ * 3 * 4, cudaMemcpyDeviceToDevice, st));
   return D3DP_OK;

@@ -249,6 +249,9 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool valid = grow < p.M;
       const bool write_a = p.out16 != nullptr;
       const int f = valid ? (grow % p.F) : 0;
+      float rs = 1.0f;  // DropPath scale of this row's branch (x * 1.0f is exact: eval results do not change)
+      if (p.row_scale && valid)
+        rs = __ldg(p.row_scale + (p.rs_mode == 1 ? (grow / (17 * p.F)) * p.F + f : grow / p.F));
 #if LNX_ABLATE == 1
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
@@ -287,7 +290,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float t = __uint_as_float(v[i]) + sprm[lcol0 + c * 32 + i] + res[i];
+          const float t = fmaf(__uint_as_float(v[i]) + sprm[lcol0 + c * 32 + i], rs, res[i]);
           if (c == 0 && i == 0) pv = t;
           const float d = t - pv;
           s1 += d;

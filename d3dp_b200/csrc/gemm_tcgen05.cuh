@@ -39,6 +39,12 @@ struct GemmParams {
   float ln_b_eps;
   const float* tpos;  // EPI_RES_LN2 only; [F,512] added after LN_a, or null
   int F;              // frames (row % F = frame index in the [S, J, F] token order)
+  // LN modes, training forward only: stochastic depth (timm DropPath, common/mixste.py:100,114-115).  The branch output
+  // acc + bias of row r is multiplied by row_scale[idx(r)] (= mask / keep_prob) before the residual add; null = none.
+  // rs_mode 1 (spatial block, one draw per (stream, frame)): idx = (r / (17 F)) * F + r % F;
+  // rs_mode 2 (temporal block, one draw per (stream, joint)): idx = r / F.
+  const float* row_scale;
+  int rs_mode;
 };
 
 constexpr int GEMM_BM = 128;

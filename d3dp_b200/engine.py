@@ -91,15 +91,22 @@ class Engine:
         return t.detach().to(self.device, torch.float32).contiguous()
 
     # ------------------------------------------------------------------ entry points
-    def denoise(self, x2d, x_t, t):
+    def drop_scale_numel(self, n_streams):
+        """Elements of the packed DropPath factor buffer d3dp_denoise takes (include/d3dp_b200.h)."""
+        return self.depth * 2 * n_streams * (self.frames + 17)
+
+    def denoise(self, x2d, x_t, t, drop_scale=None):
         x2d, x_t = self._f32(x2d), self._f32(x_t)
         t = t.detach().to(self.device, torch.int64).contiguous()
         B, H = x_t.shape[0], x_t.shape[1]
+        if drop_scale is not None:
+            drop_scale = self._f32(drop_scale)
+            assert drop_scale.numel() == self.drop_scale_numel(B * H)
         out = torch.empty_like(x_t)
         ws = self.workspace(B, H, False)
         with torch.cuda.device(self.device):
-            check(self.handle, self.lib.d3dp_denoise(self.handle, ptr(x2d), ptr(x_t), ptr(t), ptr(out), B, H, ptr(ws),
-                                                     ws.numel(), _stream()), "d3dp_denoise")
+            check(self.handle, self.lib.d3dp_denoise(self.handle, ptr(x2d), ptr(x_t), ptr(t), ptr(drop_scale), ptr(out),
+                                                     B, H, ptr(ws), ws.numel(), _stream()), "d3dp_denoise")
         return out
 
     def ddim_sample(self, x2d, x2d_flip, H, K, noise_init=None, noise_steps=None, seed=0, h_offset=0, H_total=None,
@@ -136,11 +143,12 @@ class Engine:
         """J-Agg / P-Agg.  shards=1: preds [B,K,H,F,17,3]; shards=W: preds [W,B,K,H/W,F,17,3], the rank-major output of
         the all-gather of the per-rank hypothesis shards (distributed.gather_shards)."""
         preds, traj, cam, x2d = self._f32(preds), self._f32(traj), self._f32(cam), self._f32(x2d)
-        if shards == 1:
-            B, K, H = preds.shape[0], preds.shape[1], preds.shape[2]
-        else:
-            assert preds.dim() == 7 and preds.shape[0] == shards
+        if preds.dim() == 7:  # rank-major shard buffer (a single shard is the reference layout with a leading 1)
+            assert preds.shape[0] == shards
             B, K, H = preds.shape[1], preds.shape[2], preds.shape[3] * shards
+        else:
+            assert shards == 1
+            B, K, H = preds.shape[0], preds.shape[1], preds.shape[2]
         traj = traj.reshape(B, self.frames, 3)
         if cam.dim() == 1:
             cam = cam[None].expand(B, 9).contiguous()

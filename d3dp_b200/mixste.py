@@ -52,6 +52,8 @@ class MixSTE2(nn.Module):
         C = embed_dim_ratio
         self.is_train = is_train
         self.num_frame, self.block_depth = num_frame, depth
+        # stochastic depth decay rule (common/mixste.py:186): block i of both stacks drops a branch with dpr[i]
+        self.drop_path_rates = [x.item() for x in torch.linspace(0, drop_path_rate, depth)]
         self._joints_left, self._joints_right, self._scale = list(joints_left), list(joints_right), float(scale)
         self._output_scale = float(output_scale)  # sampler outputs are stored as x0 * output_scale (3DHP: 1000)
         self.Spatial_patch_to_embedding = nn.Linear(in_chans + 3, C)
@@ -129,16 +131,40 @@ class MixSTE2(nn.Module):
         return ent[0]
 
     # ------------------------------------------------------------------ reference surface
-    def forward(self, x_2d, x_3d, t):
+    def draw_drop_masks(self, n_streams, device):
+        """The DropPath factors of one training-mode forward, drawn like timm's drop_path (per sample of the block
+        input's first axis, bernoulli(keep)/keep) in the reference's execution order: for every block i with
+        dpr[i] > 0: STEblocks[i] attention [S,F], STEblocks[i] mlp [S,F], TTEblocks[i] attention [S,17],
+        TTEblocks[i] mlp [S,17] (common/mixste.py:100,114-115).  Returns the list of depth x 4 tensors."""
+        masks = []
+        for i, rate in enumerate(self.drop_path_rates):
+            keep = 1.0 - rate
+            for n in (self.num_frame, self.num_frame, 17, 17):
+                if rate == 0.0:
+                    masks.append(torch.ones(n_streams, n, device=device))
+                else:
+                    m = torch.empty(n_streams, n, device=device).bernoulli_(keep)
+                    masks.append(m.div_(keep) if keep > 0.0 else m)
+        return masks
+
+    def forward(self, x_2d, x_3d, t, drop_masks=None):
         """common/mixste.py:278-298.  eval: x_2d [b,f,17,2], x_3d [b,h,f,17,3], t [b] -> [b,h,f,17,3];
-        train layout (is_train=True): x_3d [b,f,17,3] -> [b,f,17,3].  Forward only: the kernels keep nothing for a
-        backward pass, so a training-mode call under autograd is refused instead of returning a detached tensor."""
+        train layout (is_train=True): x_3d [b,f,17,3] -> [b,f,17,3].  In training mode (`self.training`) with a
+        non-zero drop_path_rate the residual branches are dropped per sample exactly like the reference's timm
+        DropPath (`drop_masks`: the depth x 4 factor tensors of draw_drop_masks, injected by tests; drawn otherwise).
+        Forward only: the kernels keep nothing for a backward pass, so a training-mode call under autograd is refused
+        instead of returning a detached tensor."""
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError(
                 "d3dp_b200.MixSTE2 is forward-only (sm_100a inference kernels, no backward): call it under "
                 "torch.no_grad() / in eval() mode, or train with the reference implementation")
         with torch.no_grad():
             eng = self.engine()
-            if self.is_train:
-                return eng.denoise(x_2d, x_3d[:, None], t)[:, 0]
-            return eng.denoise(x_2d, x_3d, t)
+            x_t = x_3d[:, None] if self.is_train else x_3d
+            ds = None
+            if drop_masks is None and self.training and any(r > 0 for r in self.drop_path_rates):
+                drop_masks = self.draw_drop_masks(x_t.shape[0] * x_t.shape[1], eng.device)
+            if drop_masks is not None:
+                ds = torch.cat([m.to(eng.device, torch.float32).reshape(-1) for m in drop_masks])
+            out = eng.denoise(x_2d, x_t, t, drop_scale=ds)
+            return out[:, 0] if self.is_train else out

@@ -83,10 +83,16 @@ int d3dp_time_list(int32_t num_timesteps, int32_t K, int32_t* out_host);
 /* Workspace needed by d3dp_denoise / d3dp_ddim_sample for B clips x H hypotheses (flip != 0 doubles the streams). */
 int d3dp_workspace_bytes(const d3dp_handle* h, int32_t B, int32_t H, int32_t flip, size_t* bytes);
 
-/* MixSTE2.forward, eval branch (common/mixste.py:278-298): out[B,H,F,17,3] = D(x2d[B,F,17,2], x_t[B,H,F,17,3], t[B]).
- * t is a device int64 array. */
-int d3dp_denoise(d3dp_handle* h, const float* x2d, const float* x_t, const int64_t* t, float* out, int32_t B,
-                 int32_t H, void* workspace, size_t workspace_bytes, void* stream);
+/* MixSTE2.forward (common/mixste.py:278-298): out[B,H,F,17,3] = D(x2d[B,F,17,2], x_t[B,H,F,17,3], t[B]).
+ * t is a device int64 array.  The training layout (is_train=True: x_t [B,F,17,3]) is this call with H = 1.
+ * drop_scale: NULL at evaluation (DropPath is Identity, common/diffusionpose.py:121-126).  For a training-mode forward
+ * (stochastic depth, timm DropPath at common/mixste.py:100,114-115) it holds the per-sample factors mask/keep_prob of
+ * every residual branch, float32, for block d = 0..depth-1 in execution order:
+ *   [STEblocks[d] attention: S*F][STEblocks[d] mlp: S*F][TTEblocks[d] attention: S*17][TTEblocks[d] mlp: S*17]
+ * with S = B*H streams; the spatial factors are indexed (s*F + f), the temporal ones (s*17 + j) — the first axis of
+ * the reference's '(b f) n c' / '(b n) f c' block inputs. */
+int d3dp_denoise(d3dp_handle* h, const float* x2d, const float* x_t, const int64_t* t, const float* drop_scale,
+                 float* out, int32_t B, int32_t H, void* workspace, size_t workspace_bytes, void* stream);
 
 /* D3DP.ddim_sample_flip (common/diffusionpose.py:215-256) when x2d_flip != NULL, D3DP.ddim_sample (:172-212) when it
  * is NULL.  preds[B,K,H,F,17,3] receives x_start of every step (torch.stack(preds_all, dim=1)).

@@ -65,8 +65,10 @@ def time_list(timesteps, K):
 
 
 # ----------------------------------------------------------------------------------------------- denoiser
-def _block(x, sd, pre):
-    """Block.forward + Attention.forward + Mlp.forward on x[..., N, 512] (common/mixste.py:63-82,113-115,37-43)."""
+def _block(x, sd, pre, drop=None):
+    """Block.forward + Attention.forward + Mlp.forward on x[..., N, 512] (common/mixste.py:63-82,113-115,37-43).
+    `drop` = (attention factor, mlp factor), each broadcastable to x[..., :1, :1]: timm's DropPath multiplies the
+    branch output by bernoulli(keep)/keep per sample of the block input's first axis (training only)."""
     C = x.shape[-1]
     h = Fn.layer_norm(x, (C,), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"], 1e-6)
     qkv = Fn.linear(h, sd[pre + "attn.qkv.weight"], sd[pre + "attn.qkv.bias"])
@@ -76,10 +78,12 @@ def _block(x, sd, pre):
     att = (q @ k.transpose(-2, -1)) * ((C // 8) ** -0.5)
     att = att.softmax(dim=-1)
     o = (att @ v).transpose(-2, -3).reshape(*lead, N, C)
-    x = x + Fn.linear(o, sd[pre + "attn.proj.weight"], sd[pre + "attn.proj.bias"])
+    a = Fn.linear(o, sd[pre + "attn.proj.weight"], sd[pre + "attn.proj.bias"])
+    x = x + (a if drop is None else a * drop[0])
     h = Fn.layer_norm(x, (C,), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], 1e-6)
     h = Fn.gelu(Fn.linear(h, sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"]))
-    return x + Fn.linear(h, sd[pre + "mlp.fc2.weight"], sd[pre + "mlp.fc2.bias"])
+    m = Fn.linear(h, sd[pre + "mlp.fc2.weight"], sd[pre + "mlp.fc2.bias"])
+    return x + (m if drop is None else m * drop[1])
 
 
 def time_embedding(sd, t):
@@ -93,9 +97,11 @@ def time_embedding(sd, t):
     return Fn.linear(e, sd["time_mlp.3.weight"], sd["time_mlp.3.bias"])
 
 
-def denoiser(sd, x2d, x_t, t, depth=8, taps=None):
+def denoiser(sd, x2d, x_t, t, depth=8, taps=None, drop_masks=None):
     """MixSTE2.forward, eval branch (common/mixste.py:226-298): x2d [B,F,17,2], x_t [B,H,F,17,3], t [B] int64
-    -> [B,H,F,17,3].  `taps`, if a dict, receives intermediate activations for layer-by-layer checks."""
+    -> [B,H,F,17,3].  `taps`, if a dict, receives intermediate activations for layer-by-layer checks.
+    `drop_masks` (training-mode forward): depth x 4 DropPath factor tensors in execution order — STEblocks[d]
+    attention [B*H,F], STEblocks[d] mlp [B*H,F], TTEblocks[d] attention [B*H,17], TTEblocks[d] mlp [B*H,17]."""
     B, H, F = x_t.shape[0], x_t.shape[1], x_t.shape[2]
     C = 512
     u = torch.cat((x2d[:, None].expand(B, H, F, J, 2), x_t), dim=-1)                       # :227-228
@@ -106,15 +112,19 @@ def denoiser(sd, x2d, x_t, t, depth=8, taps=None):
         taps["embed"] = x.clone()
     ln_s = (sd["Spatial_norm.weight"], sd["Spatial_norm.bias"])
     ln_t = (sd["Temporal_norm.weight"], sd["Temporal_norm.bias"])
+    def drops(d, which, n):
+        if drop_masks is None:
+            return None
+        return tuple(drop_masks[4 * d + 2 * which + i].reshape(B, H, n, 1, 1).to(x.dtype) for i in range(2))
     for d in range(depth):
-        x = _block(x, sd, f"STEblocks.{d}.")                                                # over the 17 joints
+        x = _block(x, sd, f"STEblocks.{d}.", drops(d, 0, F))                                # over the 17 joints
         x = Fn.layer_norm(x, (C,), ln_s[0], ln_s[1], 1e-6)                                  # :243,269
         if d == 0:
             x = x + sd["Temporal_pos_embed"].reshape(1, 1, F, 1, C)                         # :250
         if taps is not None:
             taps[f"S{d}"] = x.clone()
         xt = x.transpose(2, 3)                                                              # [B,H,17,F,C]
-        xt = _block(xt, sd, f"TTEblocks.{d}.")                                              # over the F frames
+        xt = _block(xt, sd, f"TTEblocks.{d}.", drops(d, 1, J))                              # over the F frames
         xt = Fn.layer_norm(xt, (C,), ln_t[0], ln_t[1], 1e-6)                                # :257,273
         x = xt.transpose(2, 3)
         if taps is not None:

@@ -25,11 +25,22 @@ def _stub(name, **kw):
 
 
 class _DropPath(torch.nn.Module):
+    """Stand-in for timm.models.layers.DropPath (timm is not installed; its drop_path is: identity unless training
+    and p > 0, else x * bernoulli(1-p)/(1-p) drawn per sample of the FIRST axis, shape (N,1,...,1)).  The factor
+    tensors are served from `queue` (filled by the caller, in execution order) so that the unmodified reference's
+    training-mode forward can be compared with the oracle on identical draws."""
+    queue = []
+
     def __init__(self, p=0.0):
         super().__init__()
+        self.drop_prob = p
 
     def forward(self, x):
-        return x
+        if self.drop_prob == 0.0 or not self.training:
+            return x
+        f = _DropPath.queue.pop(0)
+        assert f.numel() == x.shape[0], (f.shape, x.shape)
+        return x * f.reshape((x.shape[0],) + (1,) * (x.dim() - 1)).to(x.dtype)
 
 
 class _TorchProxy:
@@ -82,6 +93,22 @@ def build_reference_model(frames, H, K, state, joints_left, joints_right, scale=
     missing = model.pose_estimator.load_state_dict(state, strict=True)
     model.device = torch.device("cpu")  # ddim_sample reads self.device (reference bug)
     return model
+
+
+def run_reference_train_forward(frames, state, x2d, x_t, t, drop_masks, depth=8):
+    """The reference's MixSTE2 in TRAINING mode (is_train=True layout, DropPath 0.1 active) with injected DropPath
+    factors: `drop_masks` is the depth x 4 list of d3dp_b200.MixSTE2.draw_drop_masks; blocks whose rate is 0 are
+    nn.Identity in the reference (common/mixste.py:100) and consume nothing."""
+    dp = import_reference()
+    model = dp.D3DP(make_args(frames, depth=depth), [4, 5, 6, 11, 12, 13], [1, 2, 3, 14, 15, 16], is_train=True)
+    model.pose_estimator.load_state_dict(state, strict=True)
+    model.train()
+    rates = [x.item() for x in torch.linspace(0, 0.1, depth)]
+    _DropPath.queue = [m.reshape(-1) for d in range(depth) for m in drop_masks[4 * d:4 * d + 4] if rates[d] > 0]
+    with torch.no_grad():
+        out = model.pose_estimator(x2d, x_t, t)
+    assert not _DropPath.queue
+    return out
 
 
 def run_reference_sampler(model, x2d, x2d_flip, noise_init, noise_steps):

@@ -89,6 +89,26 @@ def main():
         same = torch.allclose(v.double(), p2[k].double(), atol=2e-6)
         print(f"P2 {k:7s} ref {v.tolist()} oracle {p2[k].tolist()} {'ok' if same else 'MISMATCH'}")
         ok &= same
+    # training-mode forward: is_train layout + stochastic depth with injected factors (common/mixste.py:100,114-115,
+    # 215-225); q_sample / prepare_diffusion_concat against the reference's (common/diffusionpose.py:260-267,290-306)
+    from d3dp_b200.mixste import MixSTE2
+    holder = MixSTE2(num_frame=F, embed_dim_ratio=512, depth=8, mlp_ratio=2., drop_path_rate=0.1)
+    torch.manual_seed(3)
+    masks = holder.draw_drop_masks(B, "cpu")
+    assert any((m == 0).any() for m in masks), "no branch dropped: pick another seed"
+    x_tr = x_t[:, 0]
+    ref_tr = rh.run_reference_train_forward(F, sd, x2d, x_tr, t, masks)
+    with torch.no_grad():
+        mine_tr = orc.denoiser(sd, x2d, x_tr[:, None], t, drop_masks=masks)[:, 0]
+    m, mx = orc.mpjpe_distance(mine_tr, ref_tr)
+    print(f"train forward + DropPath  mean {m:.3e} max {mx:.3e}")
+    ok &= mx < 1e-5
+    tt = torch.tensor([17, 803])
+    nz = torch.randn(B, F, 17, 3, generator=torch.Generator().manual_seed(8))
+    ref_q = model.q_sample(gt, tt, nz)
+    same = torch.equal(ref_q, orc.q_sample(gt, tt, nz))
+    print(f"q_sample bit-equal: {same}")
+    ok &= same
     print("ORACLE PINNED" if ok else "ORACLE MISMATCH")
     return 0 if ok else 1
 

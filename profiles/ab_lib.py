@@ -41,13 +41,16 @@ def one():
 
     jobs = []
     for name, mode, a, w in (("qkv", 0, a512, wmat(1536, 512)), ("fc1_gelu", 1, a512, wmat(1024, 512)),
-                             ("proj_res_ln", 2, a512, wmat(512, 512)), ("fc2_res_ln2", 3, a1024, wmat(512, 1024))):
+                             ("proj_res_ln", 2, a512, wmat(512, 512)), ("fc2_res_ln2", 3, a1024, wmat(512, 1024)),
+                             ("fc2_tpos", 3, a1024, wmat(512, 1024))):
         bias = (0.1 * torch.randn(w.shape[0], generator=g)).cuda()
         kw = {}
         if mode >= 2:
             kw = dict(ln_a=(ga, be, 1e-6))
         if mode == 3:
-            kw.update(ln_b=(be + 1, ga - 1, 1e-6), tpos=tpos)
+            kw.update(ln_b=(be + 1, ga - 1, 1e-6))
+        if name == "fc2_tpos":  # the one fc2 launch per forward that adds Temporal_pos_embed (block S0)
+            kw.update(tpos=tpos)
 
         def run(mode=mode, a=a, w=w, bias=bias, kw=kw, keep=False):
             if mode >= 2:
