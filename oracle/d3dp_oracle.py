@@ -303,6 +303,50 @@ def eval_data_prepare(receptive_field, inputs_2d):
     return out
 
 
+def pose_post_process(pose_pred, n_frames, receptive_field):
+    """main_3dhp.py:327-332 (+ :717-718 allocation): per-clip poses [n_clips, K, F, 17, 3] of one sequence are written
+    clip by clip into a zero [K, N, 17, 3] buffer, the last clip then overwrites the LAST F frames, and the buffer is
+    transposed to the MATLAB layout [3, 17, N, K]."""
+    F = receptive_field
+    pose_pred = np.asarray(pose_pred)
+    buf = np.zeros((pose_pred.shape[1], n_frames, J, 3))
+    for ii in range(pose_pred.shape[0] - 1):
+        buf[:, ii * F:(ii + 1) * F] = pose_pred[ii]
+    buf[:, -F:] = pose_pred[-1][:, -min(F, n_frames):] if n_frames < F else pose_pred[-1]
+    return buf.transpose(3, 2, 1, 0)
+
+
+def mpjpe_3dhp_valid(predicted, target, valid_frame, mean_pos=False):
+    """common/loss.py:109-145 mpjpe_diffusion_3dhp: P-Best (mean_pos=False) / P-Agg (mean_pos=True) error per step
+    over the VALID frames only.  predicted [B,K,H,F,17,3], target [B,F,17,3], valid_frame [B,F,1] bool -> [K]."""
+    valid = valid_frame.squeeze(2)
+    pv = predicted.permute(0, 3, 1, 2, 4, 5)[valid]                       # [n, K, H, 17, 3]
+    tv = target[valid]                                                    # [n, 17, 3]
+    K, H = pv.shape[1], pv.shape[2]
+    if not mean_pos:
+        e = torch.norm(pv - tv[:, None, None], dim=-1)                    # [n, K, H, 17]
+        e = e.permute(1, 2, 0, 3).reshape(K, H, -1).mean(-1)
+        return e.min(dim=1).values
+    e = torch.norm(pv.mean(dim=2) - tv[:, None], dim=-1)                  # [n, K, 17]
+    return e.permute(1, 0, 2).reshape(K, -1).mean(-1)
+
+
+def image_coordinates(x, w, h):
+    """common/camera.py:14-18."""
+    return (x + torch.tensor([1.0, h / w], dtype=x.dtype)) * w / 2
+
+
+def pbest_pose(preds, gt):
+    """main_3dhp.py:785-795: the single hypothesis with the lowest batch-mean error per step, gathered for every
+    clip.  preds [B,K,H,F,17,3] (root already zeroed), gt [B,F,17,3] -> pose [B,K,F,17,3], index [K]."""
+    B, K, H, F = preds.shape[:4]
+    e = torch.norm(preds - gt[:, None, None], dim=-1)
+    eh = e.permute(1, 2, 0, 3, 4).reshape(K, H, -1).mean(-1, keepdim=True)
+    idx = eh.min(dim=1, keepdim=True).indices                              # [K,1,1]
+    g = idx.unsqueeze(0).unsqueeze(-1).unsqueeze(-1).repeat(B, 1, 1, F, J, 3)
+    return torch.gather(preds, 2, g).squeeze(2), idx.reshape(K)
+
+
 def mpjpe_distance(a, b):
     """Parity metric: mean / max over all joints of the per-joint L2 distance."""
     d = torch.norm(a.double() - b.double(), dim=-1)

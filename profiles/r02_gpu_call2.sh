@@ -1,6 +1,7 @@
 #!/bin/bash
 # Round 2, GPU call 2: bench lines (c3 graph / no graph, c2), A/B of kernel variants, compute-sanitizer.
 mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q -s > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -4 gpurun_out/pytest_gpu.log
 timeout 400 python bench.py --steps 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
 D3DP_GRAPH=0 timeout 200 python bench.py --steps 3 --no-cpu-baseline > gpurun_out/bench_nograph.json 2>> gpurun_out/bench.err
 timeout 300 python bench.py --steps 5 --config c2 --no-cpu-baseline > gpurun_out/bench_c2.json 2>> gpurun_out/bench.err

@@ -349,3 +349,39 @@ def test_sequence_evaluator_on_device():
     assert all(torch.isfinite(full[k]).all() for k in ("J-Best", "P-Best", "P-Agg", "J-Agg", "P2-J-Agg"))
     assert (full["J-Best"] <= full["J-Agg"] + 1e-6).all() and (full["P2-J-Best"] <= full["P2-P-Best"] + 1e-6).all()
     assert [tuple(p.shape) for p in full["jagg_pose"]] == [(K, 11, 17, 3), (K, 60, 17, 3), (K, 81, 17, 3)]
+
+
+def test_droppath_training_forward_matches_oracle():
+    """Stochastic depth in the training-mode forward (timm DropPath 0.1 with the linear decay rule,
+    common/mixste.py:100,114-115,186): per-sample branch factors injected on both sides — the oracle's DropPath path
+    is pinned bit-exactly to the reference's (oracle/validate_against_reference.py).  Rate 0.5 here so that branches
+    are actually dropped in a 2-clip batch; eval mode ignores the rate."""
+    from d3dp_b200 import MixSTE2
+    case = load_golden("f27_flip")
+    sd, x2d, _, n0, _ = case_inputs(case)
+    m = MixSTE2(num_frame=27, embed_dim_ratio=512, depth=8, mlp_ratio=2., drop_path_rate=0.5, is_train=True)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().train()
+    torch.manual_seed(4)
+    masks = m.draw_drop_masks(2, "cuda")
+    assert len(masks) == 32 and masks[0].shape == (2, 27) and masks[2].shape == (2, 17)
+    assert torch.all(masks[0] == 1) and any((k == 0).any() for k in masks) and any((k > 1).any() for k in masks)
+    t = torch.tensor([250, 900])
+    x_t = n0[:, 0].clamp(-1.1, 1.1)
+    with torch.no_grad():
+        out = m(x2d.cuda(), x_t.cuda(), t.cuda(), drop_masks=masks)
+        ref = orc.denoiser(sd, x2d, x_t[:, None], t, drop_masks=[k.cpu() for k in masks])[:, 0]
+        plain = orc.denoiser(sd, x2d, x_t[:, None], t)[:, 0]
+    mean, mx = mpjpe_distance(out, ref)
+    print(f"\n[parity] training forward with DropPath: mean {mean:.3e} max {mx:.3e} "
+          f"(effect of the drops: {mpjpe_distance(ref, plain)[0]:.3e})")
+    assert mean < 1e-3 and mx < 1e-2 and mpjpe_distance(ref, plain)[0] > 10 * mean
+    with torch.no_grad():  # drawn inside forward when not injected: reproducible under the torch seed
+        torch.manual_seed(9)
+        a = m(x2d.cuda(), x_t.cuda(), t.cuda())
+        torch.manual_seed(9)
+        b = m(x2d.cuda(), x_t.cuda(), t.cuda())
+        assert torch.equal(a, b) and not torch.equal(a, out)
+        m.eval()
+        e = m(x2d.cuda(), x_t.cuda(), t.cuda())
+    assert mpjpe_distance(e, plain)[0] < 1e-3

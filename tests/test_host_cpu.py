@@ -307,3 +307,94 @@ def test_gelu_polynomial_in_kernel_source_meets_its_accuracy_claim():
     inside = np.abs(vd) <= 5.5                               # the fitted range; beyond it the result is -|v| 1.9e-8
     assert (err / ulp16)[inside].max() <= 0.02, (err / ulp16)[inside].max()
     assert err[~inside].max() <= 2e-7
+
+
+def _ref_module(name):
+    """Import a module of the reference tree where it exists (build container); None elsewhere (GPU box)."""
+    from oracle import ref_harness as rh
+    if not rh.available():
+        return None
+    import importlib
+    import sys
+    import types
+    rh.import_reference()
+    if "matplotlib" not in sys.modules:  # not installed; common/loss.py:1 imports one unused symbol from it
+        sys.modules["matplotlib"] = types.ModuleType("matplotlib")
+        mp = types.ModuleType("matplotlib.pyplot")
+        mp.bone = None
+        sys.modules["matplotlib.pyplot"] = mp
+    return importlib.import_module(name)
+
+
+@pytest.mark.parametrize("n_frames", [5, 27, 40, 54, 100])
+def test_3dhp_export_layout_and_stitching(n_frames):
+    """clips.export_layout_3dhp / stitch_clips_last_wins == the oracle restatement of main_3dhp.py:327-332,866-871
+    (last clip overwrites the last F frames; MATLAB layout [3,17,N,K]), for sequences shorter than, equal to and not
+    a multiple of F; the oracle restatement is itself compared with an exec of the reference's function."""
+    import numpy as np
+
+    from d3dp_b200.clips import eval_data_prepare, export_layout_3dhp, stitch_clips_last_wins
+    from oracle import d3dp_oracle as orc
+    F, K = 27, 3
+    g = torch.Generator().manual_seed(n_frames)
+    n_clips = max((n_frames + F - 1) // F, 1)
+    clip_poses = torch.randn(n_clips, K, F, 17, 3, generator=g)
+    if n_frames < F:   # what the pipeline produces for a padded short sequence: the real frames come first
+        seq = torch.randn(K, n_frames, 17, 3, generator=g)
+        clip_poses = torch.cat([seq, seq[:, -1:].expand(K, F - n_frames, 17, 3)], dim=1)[None]
+        want = seq.permute(3, 2, 1, 0).numpy()
+    else:
+        want = orc.pose_post_process(clip_poses.numpy(), n_frames, F)
+        # main_3dhp.py runs argparse and builds datasets at import: exec its function's source where the tree exists
+        src_path = "/root/reference/main_3dhp.py"
+        if os.path.exists(src_path):
+            src = open(src_path).read()
+            fn_src = src[src.index("def pose_post_process"):src.index("def cam_mm_to_pix")]
+            ns = {}
+            exec(fn_src, ns)
+            dl = ns["pose_post_process"](clip_poses.numpy(), {"k": np.zeros((K, n_frames, 17, 3))}, "k", F)
+            assert np.array_equal(dl["k"], want)
+    out = export_layout_3dhp(clip_poses, n_frames)
+    assert out.shape == (3, 17, n_frames, K)
+    assert np.allclose(out.numpy(), want)
+    st = stitch_clips_last_wins(clip_poses, n_frames)
+    assert st.shape == (K, n_frames, 17, 3) and np.allclose(st.permute(3, 2, 1, 0).numpy(), want)
+    # round trip with the clip cutter: cut -> identity per clip -> stitch gives the sequence back
+    seq = torch.randn(n_frames, 17, 3, generator=g)
+    cl, _ = eval_data_prepare(F, seq)
+    assert torch.equal(stitch_clips_last_wins(cl[:, None], n_frames)[0], seq)
+
+
+def test_valid_frame_metrics_pbest_pose_and_image_coordinates():
+    """metrics.valid_frame_metrics (common/loss.py:109-145), metrics.pbest_pose (main_3dhp.py:785-795) and
+    clips.image_coordinates (common/camera.py:14-18) against the oracle restatements, and those against the
+    reference's own functions where its tree is present."""
+    from d3dp_b200.clips import image_coordinates
+    from d3dp_b200.metrics import pbest_pose, valid_frame_metrics
+    from oracle import d3dp_oracle as orc
+    g = torch.Generator().manual_seed(2)
+    B, K, H, F = 3, 2, 4, 9
+    gt = torch.randn(B, F, 17, 3, generator=g)
+    gt[:, :, 14] = 0
+    preds = gt[:, None, None] + 0.1 * torch.randn(B, K, H, F, 17, 3, generator=g)
+    preds[:, :, :, :, 14] = 0
+    valid = torch.rand(B, F, 1, generator=g) > 0.3
+    e3d = torch.norm(preds - gt[:, None, None], dim=-1)
+    pb, pa = valid_frame_metrics(e3d, preds.mean(dim=2), gt, valid)
+    want_pb, want_pa = orc.mpjpe_3dhp_valid(preds, gt, valid), orc.mpjpe_3dhp_valid(preds, gt, valid, mean_pos=True)
+    assert torch.allclose(pb, want_pb, atol=1e-6) and torch.allclose(pa, want_pa, atol=1e-6)
+    pose, idx = orc.pbest_pose(preds, gt)
+    mine = pbest_pose(preds, idx, root_joint=14)
+    assert torch.equal(mine, pose)
+    x = torch.randn(5, 17, 2, generator=g)
+    assert torch.allclose(image_coordinates(x, 2048, 1536), orc.image_coordinates(x, 2048, 1536))
+    loss = _ref_module("common.loss")
+    if loss is not None:
+        assert torch.allclose(loss.mpjpe_diffusion_3dhp(preds, gt, valid), want_pb, atol=1e-7)
+        assert torch.allclose(loss.mpjpe_diffusion_3dhp(preds, gt, valid, mean_pos=True), want_pa, atol=1e-7)
+        cam = _ref_module("common.camera")
+        assert torch.allclose(torch.as_tensor(cam.image_coordinates(x.numpy(), 2048, 1536)).float(),
+                              orc.image_coordinates(x, 2048, 1536), atol=1e-4)
+    # no valid frame at all: NaN, like the reference's mean over an empty selection
+    nb, na = valid_frame_metrics(e3d, preds.mean(dim=2), gt, torch.zeros(B, F, 1, dtype=torch.bool))
+    assert torch.isnan(nb).all() and torch.isnan(na).all()
