@@ -123,6 +123,7 @@ def test_train_branch_runs_prepare_targets_and_refuses_autograd():
     gt = 0.5 * n0[:, 0]
     with pytest.raises(NotImplementedError):
         m(x2d.cuda(), gt.cuda())                                         # training mode + grad enabled
+    m.eval()  # keeps the is_train layout / noising branch; switches stochastic depth off (tested separately below)
     torch.manual_seed(11)
     with torch.no_grad():
         x_t, noise, t = m.prepare_targets(gt.cuda())
