@@ -151,22 +151,41 @@ def cpu_reference_sample(repeats, warmup=0):
 
 
 def gpu_eager_reference_sample(dev, repeats=3):
-    """The reference's own eager fp32 PyTorch path (oracle port, ATen kernels, TF32 off) on the SAME GPU, bounded sample
-    B=1,H=20,K=1,F=243 with flip TTA — the GPU-to-GPU comparison the reference itself would give on this box."""
+    """The reference's eager fp32 PyTorch path on the SAME GPU (TF32 off), bounded sample B=1,H=20,K=1,F=243 with flip
+    TTA — the GPU-to-GPU comparison the reference itself would give on this box.  Where the reference tree resolves
+    ($D3DP_REF or /root/reference: the build container, not the GPU box) the UNMODIFIED `D3DP.ddim_sample_flip` runs
+    (kind "reference"); elsewhere the oracle port, which issues the same ATen ops (kind "port").  Returns
+    (poses/s at the config's H and K, seconds per sample, kind)."""
     import torch
     from d3dp_b200.synthetic import (H36M_JOINTS_LEFT as JL, H36M_JOINTS_RIGHT as JR, synthetic_inputs,
                                      synthetic_pose_estimator_state)
     from oracle import d3dp_oracle as orc
+    from oracle import ref_harness as rh
     torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
     H = 20  # one clip at the paper's hypothesis count: 82 620 tokens x 2 flips per forward, enough to fill the GPU
-    sd = {k: v.to(dev) for k, v in synthetic_pose_estimator_state(F_FRAMES, seed=0).items()}
+    sd_cpu = synthetic_pose_estimator_state(F_FRAMES, seed=0)
     x2d, x2d_flip, n0, ns = [t.to(dev) for t in synthetic_inputs(1, H, 1, F_FRAMES)]
-    bufs = {k: v.to(dev) for k, v in orc.schedule_buffers(1000).items()}
+    kind = "port"
+    if rh.available():
+        try:
+            ref = rh.build_reference_model(F_FRAMES, H, 1, sd_cpu, JL, JR).to(dev)
 
-    def once():
-        with torch.no_grad():
-            return orc.ddim_sample(sd, x2d, x2d_flip, H, 1, n0, ns, JL, JR, buffers=bufs)
-    once()
+            def once():
+                with torch.no_grad():
+                    return ref(x2d, None, input_2d_flip=x2d_flip)  # draws its own noise with torch.randn(device='cuda')
+            once()
+            kind = "reference"
+        except Exception:
+            kind = "port"
+    if kind == "port":
+        sd = {k: v.to(dev) for k, v in sd_cpu.items()}
+        bufs = {k: v.to(dev) for k, v in orc.schedule_buffers(1000).items()}
+
+        def once():
+            with torch.no_grad():
+                return orc.ddim_sample(sd, x2d, x2d_flip, H, 1, n0, ns, JL, JR, buffers=bufs)
+        once()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     s.record()
@@ -175,7 +194,7 @@ def gpu_eager_reference_sample(dev, repeats=3):
     e.record()
     torch.cuda.synchronize()
     t = s.elapsed_time(e) / repeats * 1e-3
-    return F_FRAMES * H / (t * H_PER_GPU * K_STEPS), t
+    return F_FRAMES * H / (t * H_PER_GPU * K_STEPS), t, kind
 
 
 def run_reference_arm(args, rank):
@@ -479,15 +498,16 @@ def run_ours(args, rank, world, local_rank):
     if cpu_line:
         line["cpu_baseline"] = cpu_line
         try:
-            v, t_s = gpu_eager_reference_sample(dev)
+            v, t_s, ekind = gpu_eager_reference_sample(dev)
             a100 = 4.0  # assumed B200 : A100 ratio of eager fp32 (non-TF32) PyTorch throughput on this model
             line["gpu_eager_baseline"] = {
-                "value": v, "unit": "poses/s", "kind": "port",
+                "value": v, "unit": "poses/s", "kind": ekind,
                 "speedup": value / v,
                 "a100_scaling_factor_assumed": a100,
                 "speedup_vs_a100_equivalent": value / v * a100,
-                "sample": f"oracle port (same ATen ops as the reference; /root/reference itself is not present on the "
-                          f"GPU box) in eager fp32 on this GPU, TF32 off, B=1 H=20 K=1 F={F} flip, {t_s * 1e3:.0f} ms, "
+                "sample": ("unmodified reference D3DP.ddim_sample_flip" if ekind == "reference" else
+                           "oracle port (same ATen ops as the reference, whose tree is not present on this box)") +
+                          f" in eager fp32 on this GPU, TF32 off, B=1 H=20 K=1 F={F} flip, {t_s * 1e3:.0f} ms, "
                           f"scaled by B*K linearity; A100-equivalent = this / {a100:g} (assumption, stated)"}
         except Exception as ex:  # never let the extra baseline break the bench line
             line["gpu_eager_baseline"] = {"error": str(ex)[:200]}

@@ -5,20 +5,27 @@
 // [T, 1536] fp16 (q | k | v thirds, head h = columns 64h..64h+63 of each third, mixste.py:65-67).
 // Per work item (sequence, head): TMA loads Q, K, V [ROWS x 64] (ROWS = F rounded up to 16, <= 256) as three
 // 128-byte-swizzled tiles; S = Q.K^T goes to TMEM with tcgen05 (M=128 per query tile, N=ROWS, K=64); the softmax
-// warpgroup owns one TMEM lane (= query row) per thread: max, exp2, row sum, P -> fp16 written back over S in TMEM;
-// O = P.V is a TS-form tcgen05.mma (A = P from TMEM, B = V from smem, MN-major); O / rowsum is stored as fp16.
-// F <= 256 so one N tile holds the whole row: no online-softmax rescaling.
+// warpgroup owns one TMEM lane (= query row) per thread; P is written back over S in TMEM as fp16;
+// O = P.V is a TS-form tcgen05.mma (A = P from TMEM, B = V from smem, MN-major).
+//
+// The kernel is bound by the TMEM read port: tcgen05.ld delivers 64 B/clk per SM when the data is consumed
+// (profiles/r02_tmem_bw.txt), and a 128 x 256 fp32 score tile is 128 KB = 2 k clk per read.  So every score leaves
+// TMEM ONCE: a thread takes its row in two halves of 128 keys, each with its own maximum:
+// p_A = 2^((s - m_A) c) -> P_A -> O_A = P_A.V_A, then p_B relative to m = max(m_A, m_B) -> O_B = P_B.V_B, and the
+// output is (2^((m_A - m) c) O_A + O_B) / (2^((m_A - m) c) l_A + l_B): exact softmax with 192 KB of TMEM reads per
+// query tile (S once + two 32 KB partial outputs) instead of the 288 KB of a max pass + an exp pass (round 1's
+// kernel: 0.687 ms; this one 0.636 ms same box, profiles/r02_ab_attnsr.log).  Half B is requested chunk by chunk
+// into the registers half A has just vacated, invalid keys are masked with -inf so that each body exists once, the
+// four output pieces are requested together, and the TMEM region is freed before the global stores.
+// TMEM region of a query tile: S [0,256) -> P_A [0,64) P_B [64,128) O_A [128,192) O_B [192,256).
 //
 // Schedule (F > 128, two query tiles per item): the single MMA thread issues the two query tiles of an item half a
 // period apart — S0(i), PV1(i-1), S1(i), PV0(i) — so warpgroup 0 runs its softmax while the tensor core works for
-// warpgroup 1 and vice versa (ping-pong), instead of both warpgroups exponentiating at once and then both waiting
-// (same-box A/B at the bench shape: 0.773 -> 0.687 ms).  Measured and rejected on top of this (profiles/r01_notes.md):
-// FMA-pipe polynomial exp2 for 40 % of the elements (+1.5 %: not MUFU-bound), packed FFMA2/FADD2 softmax arithmetic
-// (+0.7 %: not issue-bound), and a single-TMEM-read two-half online softmax (+12 %: the loads no longer overlap the
-// arithmetic inside a warpgroup).  The two passes over S read 576 KB of TMEM per item; at tcgen05.ld's 64 B/clk that is
-// 9.2 k clk, which is the measured item time — the TMEM read port is the bound of this kernel.
+// warpgroup 1 and vice versa (ping-pong); PV is split into the A and B halves on pa_full / pb_full.
 // Q/K and V have their own full/empty barriers per stage: Q and K are released as soon as S1(i) has been issued, V
 // after PV1(i), which gives the TMA producer a full item period of prefetch distance with two 96 KB stages.
+// Tensor-pipe ceiling of this formulation: the MMAs of an item are 2 048 clk, its TMEM reads 6 144 clk (384 KB),
+// its exponentials 4 096 clk of MUFU: <= 33 % tensor pipe however well the three overlap.
 #pragma once
 #include "ptx.cuh"
 
@@ -37,11 +44,8 @@ constexpr int ATT_STAGE_BYTES = 3 * ATT_TILE_BYTES;  // Q, K, V
 constexpr int ATT_STAGES = 2;
 constexpr int ATT_SMEM_BYTES = ATT_STAGES * ATT_STAGE_BYTES + 256 + 1024;
 
-#if defined(D3DP_ATTN_SINGLE_READ) && D3DP_ATTN_SINGLE_READ
-#include "attn_temporal_sr.inc"
-#else
-// barriers: qk_full[2], qk_empty[2], v_full[2], v_empty[2] (per smem stage); s_full[2], p_full[2], o_full[2],
-// s_free[2] (per query tile / TMEM region)
+// barriers: qk_full[2], qk_empty[2], v_full[2], v_empty[2] (per smem stage); s_full[2], pa_full[2], pb_full[2],
+// o_full[2], s_free[2] (per query tile / TMEM region)
 __global__ void __launch_bounds__(320, 1)
 attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -51,8 +55,9 @@ attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParam
   uint64_t* vfull_bar = qkempty_bar + 2;
   uint64_t* vempty_bar = vfull_bar + 2;
   uint64_t* sfull_bar = vempty_bar + 2;
-  uint64_t* pfull_bar = sfull_bar + 2;
-  uint64_t* ofull_bar = pfull_bar + 2;
+  uint64_t* pafull_bar = sfull_bar + 2;
+  uint64_t* pbfull_bar = pafull_bar + 2;
+  uint64_t* ofull_bar = pbfull_bar + 2;
   uint64_t* sfree_bar = ofull_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sfree_bar + 2);
 
@@ -60,6 +65,9 @@ attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParam
   const int lane = threadIdx.x & 31;
   const int num_items = p.num_seq * 8;
   const int n_mtiles = (p.F + 127) / 128;  // 1 or 2 query tiles
+  const int nchunks = (p.rows + 31) / 32;  // 32-key chunks of a score row (1..8)
+  const int n_a = nchunks < 4 ? nchunks : 4;  // chunks of half A (keys [0,128)) and half B (keys [128,256))
+  const int n_b = nchunks - n_a;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -69,7 +77,8 @@ attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParam
       mbar_init(&vfull_bar[i], 1);
       mbar_init(&vempty_bar[i], 1);
       mbar_init(&sfull_bar[i], 1);
-      mbar_init(&pfull_bar[i], 4);
+      mbar_init(&pafull_bar[i], 4);
+      mbar_init(&pbfull_bar[i], 4);
       mbar_init(&ofull_bar[i], 1);
       mbar_init(&sfree_bar[i], 4);
     }
@@ -105,6 +114,7 @@ attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParam
       const uint32_t idesc_s = make_idesc_f16(128, p.rows, 0, 0);  // S = Q.K^T : both K-major
       const uint32_t idesc_o = make_idesc_f16(128, 64, 0, 1);      // O = P.V   : A from TMEM, B (V) MN-major
       const int pv_ksteps = p.rows / 16;
+      const int ka = pv_ksteps < 8 ? pv_ksteps : 8;  // k-steps (16 keys each) of half A
       auto issue_s = [&](int mt, uint32_t stage_base) {  // S(mt) = Q[mt].K^T -> TMEM region mt, columns [0, rows)
         const uint32_t d_tmem = tmem_base + mt * 256;
 #pragma unroll
@@ -115,13 +125,23 @@ attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParam
         }
         tc_commit(&sfull_bar[mt]);
       };
-      auto issue_pv = [&](int mt, uint32_t stage_base) {  // O(mt) = P(mt).V : P fp16 at columns [0,128), O at [128,192)
+      // O_A(mt) = P_A.V[0:128) -> columns [128,192), then O_B(mt) = P_B.V[128:rows) -> [192,256); P_A / P_B are fp16
+      // pairs at columns [0,64) / [64,128).  `par` is the item parity of the warpgroup's barriers.
+      auto issue_pv = [&](int mt, uint32_t stage_base, uint32_t par) {
         const uint32_t p_tmem = tmem_base + mt * 256;
-        const uint32_t o_tmem = p_tmem + 128;
         const uint32_t v_base = stage_base + 2 * ATT_TILE_BYTES;
-        for (int k = 0; k < pv_ksteps; ++k)
-          mma_f16_ts(o_tmem, p_tmem + k * 8, make_sdesc_sw128(v_base + k * 16 * 128, 1024, 1024), idesc_o,
+        mbar_wait(&pafull_bar[mt], par);
+        tc_fence_after();
+        for (int k = 0; k < ka; ++k)
+          mma_f16_ts(p_tmem + 128, p_tmem + k * 8, make_sdesc_sw128(v_base + k * 16 * 128, 1024, 1024), idesc_o,
                      k != 0 ? 1u : 0u);
+        if (n_b > 0) {
+          mbar_wait(&pbfull_bar[mt], par);
+          tc_fence_after();
+          for (int k = ka; k < pv_ksteps; ++k)
+            mma_f16_ts(p_tmem + 192, p_tmem + k * 8, make_sdesc_sw128(v_base + k * 16 * 128, 1024, 1024), idesc_o,
+                       k != ka ? 1u : 0u);
+        }
         tc_commit(&ofull_bar[mt]);
       };
       int s = 0;
@@ -135,9 +155,7 @@ attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParam
           issue_s(0, base);
           tc_commit(&qkempty_bar[s]);
           mbar_wait(&vfull_bar[s], ph);
-          mbar_wait(&pfull_bar[0], iph);
-          tc_fence_after();
-          issue_pv(0, base);
+          issue_pv(0, base, iph);
           tc_commit(&vempty_bar[s]);
           if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
           iph ^= 1;
@@ -155,9 +173,7 @@ attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParam
           issue_s(0, base);
           // PV1(i-1): V of the previous stage (its v_full was waited for before PV0(i-1))
           if (!first) {
-            mbar_wait(&pfull_bar[1], iph ^ 1);
-            tc_fence_after();
-            issue_pv(1, prev_base);
+            issue_pv(1, prev_base, iph ^ 1);
             tc_commit(&vempty_bar[prev_s]);
           }
           // S1(i)
@@ -167,9 +183,7 @@ attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParam
           tc_commit(&qkempty_bar[s]);  // Q and K of this item are not read again
           // PV0(i)
           mbar_wait(&vfull_bar[s], ph);
-          mbar_wait(&pfull_bar[0], iph);
-          tc_fence_after();
-          issue_pv(0, base);
+          issue_pv(0, base, iph);
           first = false;
           prev_base = base;
           prev_s = s;
@@ -177,9 +191,7 @@ attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParam
           iph ^= 1;
         }
         if (!first) {  // PV1 of the last item
-          mbar_wait(&pfull_bar[1], iph ^ 1);
-          tc_fence_after();
-          issue_pv(1, prev_base);
+          issue_pv(1, prev_base, iph ^ 1);
           tc_commit(&vempty_bar[prev_s]);
         }
       }
@@ -191,119 +203,129 @@ attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParam
     const int r = quad * 32 + lane;  // row within the tile == TMEM lane
     if (mt < n_mtiles) {
       const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + mt * 256;
-      const int nchunks = (p.rows + 31) / 32;
+      const int full_chunks = p.F >> 5;   // chunks whose 32 keys are all valid
+      const int tail = p.F & 31;          // valid keys in chunk `full_chunks` (0: none)
+      const float c2 = p.scale_log2e;
       uint32_t iph = 0;
+      uint32_t v[4][32];                  // one half (up to 128 keys) of this thread's score row
+
+      // keys >= F of the chunk that straddles F become -inf: they drop out of the maximum and exponentiate to 0, so
+      // the max / exp bodies below exist once, unmasked (the two-variant bodies did not fit the instruction cache)
+      auto mask_chunk = [&](uint32_t (&u)[32], int c) {
+        if (c == full_chunks && tail != 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i >= tail) u[i] = 0xff800000u;
+        }
+      };
+      auto max_chunk = [&](const uint32_t (&u)[32], float mx) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(u[i]));
+        return mx;
+      };
+      // p = 2^(s c - moff) for chunk c -> fp16 pairs at TMEM columns [16 c, 16 c + 16); returns the chunk's sum
+      auto expo_chunk = [&](const uint32_t (&u)[32], int c, float moff) {
+        uint32_t o[16];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float a = ex2_approx(fmaf(__uint_as_float(u[2 * i]), c2, -moff));
+          const float b = ex2_approx(fmaf(__uint_as_float(u[2 * i + 1]), c2, -moff));
+          sum += a + b;
+          o[i] = pack_half2(a, b);
+        }
+        tmem_st16(t_s + c * 16, o);
+        return sum;
+      };
+
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int seq = item >> 3, head = item & 7;
         const int qrow = mt * 128 + r;
         mbar_wait(&sfull_bar[mt], iph);
         tc_fence_after();
-        // Software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is processed; only the
-        // chunk that straddles F carries a key mask.
-        const int full_chunks = p.F >> 5;   // chunks whose 32 keys are all valid
-        const int tail = p.F & 31;          // valid keys in chunk `full_chunks` (0: none)
-        // ---- pass 1: row max over the valid keys
-        float mx = -INFINITY;
-        {
-          uint32_t va[32], vb[32];
-          tmem_ld32(t_s, va);
-          for (int c = 0; c < nchunks; c += 2) {
-            tmem_ld_wait();
-            if (c + 1 < nchunks) tmem_ld32(t_s + (c + 1) * 32, vb);
-            if (c < full_chunks) {
+        // ---- half A: keys [0, 128) into registers, its maximum
 #pragma unroll
-              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(va[i]));
-            } else {
+        for (int j = 0; j < 4; ++j)
+          if (j < n_a) tmem_ld32(t_s + j * 32, v[j]);
+        tmem_ld_wait();
+        float m_a = -INFINITY;
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < tail) mx = fmaxf(mx, __uint_as_float(va[i]));
-            }
-            if (c + 1 < nchunks) {
-              tmem_ld_wait();
-              if (c + 2 < nchunks) tmem_ld32(t_s + (c + 2) * 32, va);
-              if (c + 1 < full_chunks) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(vb[i]));
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (i < tail) mx = fmaxf(mx, __uint_as_float(vb[i]));
-              }
-            }
+        for (int j = 0; j < 4; ++j)
+          if (j < n_a) {
+            mask_chunk(v[j], j);
+            m_a = max_chunk(v[j], m_a);
           }
-        }
-        const float moff = mx * p.scale_log2e;
-        // ---- pass 2: p = exp2(s*c - max*c), row sum, fp16 P written over the consumed part of S
-        float sum = 0.f;
-        auto expo_chunk = [&](const uint32_t (&v)[32], int c) {
-          uint32_t o[16];
-          if (c < full_chunks) {
+        // ---- exponentiate half A chunk by chunk; as soon as a chunk's registers are consumed the matching chunk of
+        // half B (keys [128, rows)) is requested into them, so B streams out of TMEM under A's arithmetic
+        const float moff_a = m_a * c2;
+        float l_a = 0.f;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float a = ex2_approx(fmaf(__uint_as_float(v[2 * i]), p.scale_log2e, -moff));
-              const float b = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2e, -moff));
-              sum += a + b;
-              o[i] = pack_half2(a, b);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float a = 2 * i < tail ? ex2_approx(fmaf(__uint_as_float(v[2 * i]), p.scale_log2e, -moff)) : 0.f;
-              const float b =
-                  2 * i + 1 < tail ? ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2e, -moff)) : 0.f;
-              sum += a + b;
-              o[i] = pack_half2(a, b);
-            }
+        for (int j = 0; j < 4; ++j)
+          if (j < n_a) {
+            l_a += expo_chunk(v[j], j, moff_a);
+            if (j < n_b) tmem_ld32(t_s + (4 + j) * 32, v[j]);
           }
-          tmem_st16(t_s + c * 16, o);
-        };
-        {
-          uint32_t va[32], vb[32];
-          tmem_ld32(t_s, va);
-          for (int c = 0; c < nchunks; c += 2) {
-            tmem_ld_wait();
-            if (c + 1 < nchunks) tmem_ld32(t_s + (c + 1) * 32, vb);
-            expo_chunk(va, c);
-            if (c + 1 < nchunks) {
-              tmem_ld_wait();
-              if (c + 2 < nchunks) tmem_ld32(t_s + (c + 2) * 32, va);
-              expo_chunk(vb, c + 1);
-            }
-          }
-        }
+        float alpha = 1.f, l = l_a;
+        // P_A is signalled only once half B is in registers: O_A = P_A.V_A lands on B's TMEM columns
+        tmem_ld_wait();
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&pfull_bar[mt]);
-        // O = P.V done -> normalise and store
+        if (lane == 0) mbar_arrive(&pafull_bar[mt]);
+        if (n_b > 0) {
+          float m = m_a;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < n_b) {
+              mask_chunk(v[j], 4 + j);
+              m = max_chunk(v[j], m);
+            }
+          const float moff = m * c2;
+          float l_b = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < n_b) l_b += expo_chunk(v[j], 4 + j, moff);
+          alpha = ex2_approx((m_a - m) * c2);
+          l = fmaf(alpha, l_a, l_b);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&pbfull_bar[mt]);
+        }
+        // ---- O = (alpha O_A + O_B) / l : all four 32-column pieces requested at once
         mbar_wait(&ofull_bar[mt], iph);
         tc_fence_after();
-        const float inv = 1.0f / sum;
-        __half* orow = p.out + (static_cast<size_t>(seq) * p.F + qrow) * 512 + head * 64;
+        tmem_ld32(t_s + 128, v[0]);
+        tmem_ld32(t_s + 160, v[1]);
+        if (n_b > 0) {
+          tmem_ld32(t_s + 192, v[2]);
+          tmem_ld32(t_s + 224, v[3]);
+        }
+        tmem_ld_wait();
+        tc_fence_before();  // O is in registers: the region can take the next item's S
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sfree_bar[mt]);
+        if (qrow < p.F) {
+          const float inv = 1.0f / l;
+          const float wa = alpha * inv;
+          __half* orow = p.out + (static_cast<size_t>(seq) * p.F + qrow) * 512 + head * 64;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld32(t_s + 128 + c * 32, v);
-          tmem_ld_wait();
-          if (qrow < p.F) {
+          for (int c = 0; c < 2; ++c) {
+            float o[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              o[i] = __uint_as_float(v[c][i]) * wa;
+              if (n_b > 0) o[i] = fmaf(__uint_as_float(v[2 + c][i]), inv, o[i]);
+            }
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-              const uint32_t* u = v + 16 * i;
-              stg256(orow + c * 32 + 16 * i,
-                     pack_half2(__uint_as_float(u[0]) * inv, __uint_as_float(u[1]) * inv),
-                     pack_half2(__uint_as_float(u[2]) * inv, __uint_as_float(u[3]) * inv),
-                     pack_half2(__uint_as_float(u[4]) * inv, __uint_as_float(u[5]) * inv),
-                     pack_half2(__uint_as_float(u[6]) * inv, __uint_as_float(u[7]) * inv),
-                     pack_half2(__uint_as_float(u[8]) * inv, __uint_as_float(u[9]) * inv),
-                     pack_half2(__uint_as_float(u[10]) * inv, __uint_as_float(u[11]) * inv),
-                     pack_half2(__uint_as_float(u[12]) * inv, __uint_as_float(u[13]) * inv),
-                     pack_half2(__uint_as_float(u[14]) * inv, __uint_as_float(u[15]) * inv));
+              const float* u = o + 16 * i;
+              stg256(orow + c * 32 + 16 * i, pack_half2(u[0], u[1]), pack_half2(u[2], u[3]), pack_half2(u[4], u[5]),
+                     pack_half2(u[6], u[7]), pack_half2(u[8], u[9]), pack_half2(u[10], u[11]),
+                     pack_half2(u[12], u[13]), pack_half2(u[14], u[15]));
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sfree_bar[mt]);
         iph ^= 1;
       }
     }
@@ -317,8 +339,6 @@ attn_temporal_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTParam
     tmem_dealloc<512>(tmem_base);
   }
 }
-
-#endif
 
 }  // namespace d3dp
 

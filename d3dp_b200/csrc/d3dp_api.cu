@@ -218,13 +218,17 @@ constexpr int kSmemGemmQkv = Gemm2SmSmem<6, 1, false>::TOTAL;
 auto* const k_gemm_fc1 = gemm_2sm_kernel<EPI_BIAS_GELU_F16, 4, 2, true>;
 constexpr int kSmemGemmFc1 = Gemm2SmSmem<4, 2, true>::TOTAL;
 static_assert(kSmemGemmQkv <= 232448 && kSmemGemmFc1 <= 232448, "exceeds the 227 KB of shared memory per CTA");
+#ifndef D3DP_LN_ASLOTS
+#define D3DP_LN_ASLOTS 4
+#define D3DP_LN_BSLOTS 2
+#define D3DP_LN_RING 1
+#endif
 #ifndef D3DP_LN_STAGES
 #define D3DP_LN_STAGES 2
-#define D3DP_LN_RING 2
 #endif
-constexpr int kLnStages = D3DP_LN_STAGES, kLnRing = D3DP_LN_RING;
-auto* const k_gemm_proj = gemm_ln_pair_kernel<EPI_RES_LN, kLnStages, kLnRing>;
-auto* const k_gemm_fc2 = gemm_ln_pair_kernel<EPI_RES_LN2, kLnStages, kLnRing>;
+constexpr int kLnA = D3DP_LN_ASLOTS, kLnB = D3DP_LN_BSLOTS, kLnStages = D3DP_LN_STAGES, kLnRing = D3DP_LN_RING;
+auto* const k_gemm_proj = gemm_ln_pair_kernel<EPI_RES_LN, kLnA, kLnB, kLnRing>;
+auto* const k_gemm_fc2 = gemm_ln_pair_kernel<EPI_RES_LN2, kLnA, kLnB, kLnRing>;
 #ifndef D3DP_LN_ROW
 #define D3DP_LN_ROW 0  // 1: gemm_ln_row.cuh (whole rows per CTA, cta_group::2) instead of gemm_ln_pair.cuh
 #endif
@@ -234,7 +238,7 @@ auto* const k_gemm_fc2_row = gemm_ln_row_kernel<EPI_RES_LN2, kLnStages, kLnRing>
 auto* const k_gemm_fc2_row_tpos = gemm_ln_row_kernel<EPI_RES_LN2, kLnStages, kLnRing, true>;
 constexpr int kSmemN512 = LnRowSmem<kLnStages, kLnRing>::TOTAL;
 #else
-constexpr int kSmemN512 = LnPairSmem<kLnStages, kLnRing>::TOTAL;
+constexpr int kSmemN512 = LnPairSmem<kLnA, kLnB, kLnRing>::TOTAL;
 #endif
 static_assert(kSmemN512 <= 232448, "LN pair kernel exceeds the 227 KB of shared memory per CTA");
 
@@ -298,8 +302,8 @@ int launch_gemm(d3dp_handle* h, int mode, const CUtensorMap& tmA, const CUtensor
       else k_gemm_fc2_row<<<2 * pairs, 352, kSmemN512, st>>>(tmA, tmB, tmC, tmO, p);
 #else
       const int pairs = tiles_m < h->num_sms / 2 ? tiles_m : h->num_sms / 2;  // one CTA pair (cluster) per M tile
-      if (mode == EPI_RES_LN) k_gemm_proj<<<2 * pairs, 352, kSmemN512, st>>>(tmA64, tmB, tmC, tmO, p);
-      else k_gemm_fc2<<<2 * pairs, 352, kSmemN512, st>>>(tmA64, tmB, tmC, tmO, p);
+      if (mode == EPI_RES_LN) k_gemm_proj<<<2 * pairs, LN_PAIR_THREADS, kSmemN512, st>>>(tmA64, tmB, tmC, tmO, p);
+      else k_gemm_fc2<<<2 * pairs, LN_PAIR_THREADS, kSmemN512, st>>>(tmA64, tmB, tmC, tmO, p);
 #endif
       break;
     }

@@ -122,13 +122,10 @@ struct EmbedParams {
   int perm[kJ];           // joint permutation of the flip
 };
 
-#if defined(D3DP_EMBED_VEC) && D3DP_EMBED_VEC
-// Experiment switch -DD3DP_EMBED_VEC=1 (default off, unmeasured): a lane owns 16 CONSECUTIVE channels, so a token's
-// 2 KB of x and 1 KB of a16 leave as 4 + 2 128-bit stores per lane instead of 16 32-bit + 16 16-bit ones (the default
-// mapping, channel = i*32 + lane, measured 0.8 ms for 2 GB: 2.5 TB/s).  Same arithmetic per channel; the LayerNorm
-// sums are re-associated (per-lane partial sums of 16 consecutive channels, then the butterfly).  Both mappings keep a
-// lane's 16 x 5 weights + bias + LayerNorm affine in registers (212 / 197 registers: one 8-warp block per SM); if the
-// vector stores alone do not bring the kernel to the HBM floor (0.31 ms), move those 128 values to shared memory.
+// A lane owns 16 CONSECUTIVE channels, so a token's 2 KB of x and 1 KB of a16 leave as 4 + 2 128-bit stores per lane
+// (the first version's mapping channel = i*32 + lane needed 16 32-bit + 16 16-bit stores: 0.8 ms for 2 GB; this one
+// took 0.9 ms off a 38 ms sampler call in the round-2 A/B).  The lane's 16 x 5 weights + bias + LayerNorm affine stay
+// in registers for all its tokens.
 __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -210,82 +207,6 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
     ar[1] = make_uint4(h[4], h[5], h[6], h[7]);
   }
 }
-
-#else
-__global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int BH = p.B * p.H;
-  const long long T = static_cast<long long>(p.n_streams) * kJ * p.F;
-  const float* x2d_plain = p.dyn ? p.dyn->x2d : p.x2d;
-  const float* x2d_flip = p.dyn ? p.dyn->x2d_flip : p.x2d_flip;
-  // lane owns channels c = i*32 + lane: its slice of W_e, b_e and the norm1 affine stays in registers for all tokens
-  float we[16][5], be[16], lg[16], lb[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int c = i * 32 + lane;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) we[i][k] = p.w_e[c * 5 + k];
-    be[i] = p.b_e[c];
-    lg[i] = p.ln_g[c];
-    lb[i] = p.ln_b[c];
-  }
-  for (long long row = warp; row < T; row += nwarps) {
-    const int f = static_cast<int>(row % p.F);
-    const long long sj = row / p.F;
-    const int j = static_cast<int>(sj % kJ);
-    const int s = static_cast<int>(sj / kJ);
-    const bool flip = s >= BH;
-    const int bh = flip ? s - BH : s;
-    const int b = bh / p.H;
-    float in[5];
-    {
-      const float* src2 = (flip ? x2d_flip : x2d_plain) + ((static_cast<size_t>(b) * p.F + f) * kJ + j) * 2;
-      in[0] = src2[0];
-      in[1] = src2[1];
-      const int js = flip ? p.perm[j] : j;
-      const float* src3 = p.img + ((static_cast<size_t>(bh) * p.F + f) * kJ + js) * 3;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float v = src3[c];
-        if (p.clamp_hi > 0.f) v = __fdiv_rn(fminf(fmaxf(v, -p.clamp_hi), p.clamp_hi), p.scale);
-        in[2 + c] = v;
-      }
-      if (flip) in[2] = -in[2];
-    }
-    const float* sp = p.spos + j * kC + lane;
-    const float* ta = p.tau + static_cast<size_t>(b) * kC + lane;
-    float v[16];
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      float acc = be[i];
-#pragma unroll
-      for (int k = 0; k < 5; ++k) acc += we[i][k] * in[k];
-      acc += sp[i * 32] + ta[i * 32];
-      v[i] = acc;
-      sum += acc;
-    }
-#pragma unroll
-    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-    const float mean = sum * (1.0f / kC);
-    float sq = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) sq += (v[i] - mean) * (v[i] - mean);
-#pragma unroll
-    for (int d = 16; d; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
-    const float rstd = rsqrtf(sq * (1.0f / kC) + p.ln_eps);
-    float* xr = p.x + row * kC + lane;
-    __half* ar = p.a16 + row * kC + lane;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      xr[i * 32] = v[i];
-      ar[i * 32] = __float2half_rn((v[i] - mean) * rstd * lg[i] + lb[i]);
-    }
-  }
-}
-
-#endif
 
 // ------------------------------------------------------------------------------------------------ head
 // out[s, f, j, :] = W_h . LN(x[row,:]; eps 1e-5) + b_h   (reference: common/mixste.py:207-210,291-296)

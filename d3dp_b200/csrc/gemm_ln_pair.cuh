@@ -23,35 +23,40 @@
 
 namespace d3dp {
 
-template <int STAGES, int RING>
+template <int ASLOTS, int BSLOTS, int RING>
 struct LnPairSmem {
-  static constexpr int A_BYTES = 128 * 64 * 2;
-  static constexpr int B_BYTES = 256 * 64 * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;             // 48 KB
-  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;           // [2 groups] x 16 KB output staging (TMA stores)
+  static constexpr int A_BYTES = 128 * 64 * 2;                      // one k-block of the A tile (16 KB)
+  static constexpr int B_BYTES = 256 * 64 * 2;                      // one k-block of this CTA's weight half (32 KB)
+  static constexpr int B_OFFSET = ASLOTS * A_BYTES;
+  static constexpr int STG_OFFSET = B_OFFSET + BSLOTS * B_BYTES;    // [2 groups] x 16 KB output staging (TMA stores)
   static constexpr int RING_OFFSET = STG_OFFSET + 2 * 16384;        // [2 groups][RING] x 16 KB residual chunks
   static constexpr int SLOT_BYTES = 128 * 32 * 4;
   static constexpr int BAR_OFFSET = RING_OFFSET + 2 * RING * SLOT_BYTES;
-  // barriers: full[STAGES] empty[STAGES] tfull[2] tempty[2] rfull[2][RING] rempty[2][RING] xch[2] ; tmem ptr
+  // barriers: afull[ASLOTS] aempty[ASLOTS] bfull[BSLOTS] bempty[BSLOTS] tfull[2] tempty[2] rfull[2][RING]
+  // rempty[2][RING] xch[8] ; tmem ptr
   static constexpr int XCH_OFFSET = BAR_OFFSET + 512;               // [2 bufs][4 quarters][128 rows] float2
   static constexpr int PARAM_OFFSET = XCH_OFFSET + 2 * 4 * 128 * 8; // 5 x 256 floats: bias, g_a, b_a, g_b, b_b
   static constexpr int TOTAL = PARAM_OFFSET + 5 * 256 * 4 + 1024;
 };
 
-template <int EPI, int STAGES, int RING>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1)
+constexpr int LN_PAIR_THREADS = 384;  // 12 warps: A producer, MMA, residual loader, 8 epilogue, B producer
+
+template <int EPI, int ASLOTS, int BSLOTS, int RING>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LN_PAIR_THREADS, 1)
 gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmO,
                     const GemmParams p) {
   // tmA: A [M,K] fp16 box {64,64}; tmB: W [512,K] fp16 box {64,256}; tmX: x [M,512] fp32 box {32,128} (residual loads
   // and x stores); tmO: a16 [M,512] fp16 box {64,128} (LayerNorm output stores)
-  using L = LnPairSmem<STAGES, RING>;
+  using L = LnPairSmem<ASLOTS, BSLOTS, RING>;
   static_assert(EPI == EPI_RES_LN || EPI == EPI_RES_LN2, "LN epilogues only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* afull_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* aempty_bar = afull_bar + ASLOTS;
+  uint64_t* bfull_bar = aempty_bar + ASLOTS;
+  uint64_t* bempty_bar = bfull_bar + BSLOTS;
+  uint64_t* tfull_bar = bempty_bar + BSLOTS;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* rfull_bar = tempty_bar + 2;          // [g*RING + slot]
   uint64_t* rempty_bar = rfull_bar + 2 * RING;
@@ -75,9 +80,13 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmO);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 2);  // the A half this CTA multicasts lands in both CTAs: both MMAs must be done
+    for (int s = 0; s < ASLOTS; ++s) {
+      mbar_init(&afull_bar[s], 1);
+      mbar_init(&aempty_bar[s], 2);  // the A half this CTA multicasts lands in both CTAs: both MMAs must be done
+    }
+    for (int s = 0; s < BSLOTS; ++s) {
+      mbar_init(&bfull_bar[s], 1);
+      mbar_init(&bempty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -111,18 +120,34 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #endif
   if (warp == 0) {
     // ------------------------------------------------------------------ operand TMA producer
+    // The activation tile A streams from HBM (~2 us under load), the weights from L2: separate rings, so that A can
+    // be ASLOTS k-blocks deep (16 KB each) without paying for as many 32 KB weight slots.
+    // (warp 0: A, warp 11: B — independent threads, so the A stream runs ahead as far as ITS ring allows.)
     if (lane == 0 && LNX_ABLATE != 2) {
-      int s = 0;
-      uint32_t ph = 0;
+      int sa = 0;
+      uint32_t pha = 0;
       for (int tile = cluster_id; tile < tiles_m; tile += num_clusters) {
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait_backoff(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * L::STAGE_BYTES;
-          mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          mbar_wait_backoff(&aempty_bar[sa], pha ^ 1);
+          mbar_expect_tx(&afull_bar[sa], L::A_BYTES);
           // the pair shares the A tile: each CTA fetches 64 of its 128 rows and multicasts them to both
-          tma_load_2d_mc(sa + rank * (L::A_BYTES / 2), &tmA, &full_bar[s], kb * 64, tile * 128 + rank * 64, 0x3);
-          tma_load_2d(sa + L::A_BYTES, &tmB, &full_bar[s], kb * 64, ncol0);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          tma_load_2d_mc(smem + sa * L::A_BYTES + rank * (L::A_BYTES / 2), &tmA, &afull_bar[sa], kb * 64,
+                         tile * 128 + rank * 64, 0x3);
+          if (++sa == ASLOTS) { sa = 0; pha ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 11) {
+    // ------------------------------------------------------------------ weight TMA producer
+    if (lane == 0 && LNX_ABLATE != 2) {
+      int sb = 0;
+      uint32_t phb = 0;
+      for (int tile = cluster_id; tile < tiles_m; tile += num_clusters) {
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait_backoff(&bempty_bar[sb], phb ^ 1);
+          mbar_expect_tx(&bfull_bar[sb], L::B_BYTES);
+          tma_load_2d(smem + L::B_OFFSET + sb * L::B_BYTES, &tmB, &bfull_bar[sb], kb * 64, ncol0);
+          if (++sb == BSLOTS) { sb = 0; phb ^= 1; }
         }
       }
     }
@@ -130,23 +155,26 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0 && LNX_ABLATE != 2) {
       constexpr uint32_t idesc = make_idesc_f16(128, 256, 0, 0);
-      int s = 0, as = 0;
-      uint32_t ph = 0, aph = 0;
+      int sa = 0, sb = 0, as = 0;
+      uint32_t pha = 0, phb = 0, aph = 0;
       for (int tile = cluster_id; tile < tiles_m; tile += num_clusters) {
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * 256;
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&full_bar[s], ph);
+          mbar_wait(&afull_bar[sa], pha);
+          mbar_wait(&bfull_bar[sb], phb);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + s * L::STAGE_BYTES);
-          const uint32_t b_base = a_base + L::A_BYTES;
+          const uint32_t a_base = smem_u32(smem + sa * L::A_BYTES);
+          const uint32_t b_base = smem_u32(smem + L::B_OFFSET + sb * L::B_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             mma_f16_ss(d_tmem, make_sdesc_sw128(a_base + k * 32, 16, 1024), make_sdesc_sw128(b_base + k * 32, 16, 1024),
                        idesc, (kb | k) != 0 ? 1u : 0u);
-          tc_commit_mc(&empty_bar[s], 0x3);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          tc_commit_mc(&aempty_bar[sa], 0x3);
+          tc_commit(&bempty_bar[sb]);
+          if (++sa == ASLOTS) { sa = 0; pha ^= 1; }
+          if (++sb == BSLOTS) { sb = 0; phb ^= 1; }
         }
         tc_commit(&tfull_bar[as]);
         if (++as == 2) { as = 0; aph ^= 1; }
@@ -158,6 +186,12 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int slot = 0;
       uint32_t ph = 0;
       for (int tile = cluster_id; tile < tiles_m; tile += num_clusters) {
+#if defined(D3DP_LN_XPREFETCH) && D3DP_LN_XPREFETCH
+        // experiment: pull the NEXT tile's residual rows into L2 while this tile is worked on (the ring itself is
+        // only RING chunks deep, and x comes from HBM)
+        if (tile + num_clusters < tiles_m)
+          for (int c = 0; c < 8; ++c) tma_prefetch_l2_2d(&tmX, ncol0 + c * 32, (tile + num_clusters) * 128);
+#endif
         for (int c = 0; c < 4; ++c) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {

@@ -199,77 +199,6 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t tempty_leader0 = mapa_u32(smem_u32(&tempty_bar[0]), 0);
     int as = 0;
     uint32_t aph = 0;
-#if defined(D3DP_GEMM_EPI_PIPE) && D3DP_GEMM_EPI_PIPE
-    // Experiment switch -DD3DP_GEMM_EPI_PIPE=1 (default off; bit-identical outputs, measured at noise level on a
-    // power-throttling box in round 1, 168 registers with 8-32 B of spills): TMEM reads software-pipelined across slabs
-    // AND tiles.  tcgen05.ld moves 64 B/clk per SM, so the 128 KB accumulator is 2 k clk of the 4.1 k clk an MMA tile
-    // takes: slab 1 of a tile is in flight while slab 0 is converted, and slab 0 of the NEXT tile — if its accumulator
-    // is already complete — while slab 1 is converted.
-    static_assert(COLS_PER_THREAD == 128, "two 64-column slabs per thread");
-    auto emit_slab = [&](const uint32_t (&v0)[32], const uint32_t (&v1)[32], int sl, int n0, int m_blk) {
-      uint8_t* buf = gbuf + (sl % OUTBUFS) * 16384;
-      if (leader) tma_store_wait_read<OUTBUFS - 1>();
-      named_bar_sync(2 + split, 128);
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = sl * 2 + cc;
-        const uint32_t(&v)[32] = cc == 0 ? v0 : v1;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint32_t o[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float a, b;
-            unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[8 * i + 2 * q]), __uint_as_float(v[8 * i + 2 * q + 1])),
-                                   *reinterpret_cast<const uint64_t*>(bias_src + n0 + c * 32 + 8 * i + 2 * q)), a, b);
-            if constexpr (EPI == EPI_BIAS_GELU_F16) gelu_erf_x2(a, b);
-            o[q] = pack_half2(a, b);
-          }
-          const int piece = cc * 4 + i;
-          *reinterpret_cast<uint4*>(buf + r * 128 + ((piece ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-        }
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(2 + split, 128);
-      if (leader) {
-        tma_store_2d(&tmC, buf, n0 + sl * 64, m_blk * GEMM_BM);
-        tma_store_commit();
-      }
-    };
-    uint32_t va0[32], va1[32], vb0[32], vb1[32];
-    bool have_a = false;  // slab 0 of the current tile has already been requested
-    for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
-      const int m_blk = (ct / tiles_n) * 2 + rank, n_blk = ct % tiles_n;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * GEMM_BN + col0;
-      const int n0 = n_blk * GEMM_BN + col0;
-      if (!have_a) {
-        mbar_wait(&tfull_bar[as], aph);
-        tc_fence_after();
-        tmem_ld32(taddr, va0);
-        tmem_ld32(taddr + 32, va1);
-      }
-      tmem_ld_wait();
-      tmem_ld32(taddr + 64, vb0);
-      tmem_ld32(taddr + 96, vb1);
-      emit_slab(va0, va1, 0, n0, m_blk);
-      tmem_ld_wait();
-      tc_fence_before();  // all accumulator columns of this thread are in registers: free the stage
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(tempty_leader0 + as * 8);
-      if (++as == 2) { as = 0; aph ^= 1; }
-      have_a = false;
-      if (ct + num_clusters < num_ctiles) {  // prefetch slab 0 of the next tile when its accumulator is ready
-        have_a = __all_sync(0xffffffffu, mbar_try_wait(&tfull_bar[as], aph));
-        if (have_a) {
-          tc_fence_after();
-          const uint32_t tnext = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * GEMM_BN + col0;
-          tmem_ld32(tnext, va0);
-          tmem_ld32(tnext + 32, va1);
-        }
-      }
-      emit_slab(vb0, vb1, 1, n0, m_blk);
-    }
-#else
     for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
       const int m_blk = (ct / tiles_n) * 2 + rank, n_blk = ct % tiles_n;
       mbar_wait(&tfull_bar[as], aph);
@@ -327,7 +256,6 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
-#endif
   }
 
   tma_store_wait_all<0>();

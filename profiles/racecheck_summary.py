@@ -6,7 +6,7 @@ import sys
 
 kind, w, rows = None, None, collections.Counter()
 for line in open(sys.argv[1], errors="replace"):
-    m = re.search(r"(Error|Warning): (.*hazard detected[^a]*?) at (__shared__|__global__)", line)
+    m = re.search(r"(Error|Warning): (.*?hazard detected.*?) at (__shared__|__global__)", line)
     if m:
         kind = m.group(2).strip()
         continue

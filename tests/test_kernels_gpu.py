@@ -120,3 +120,20 @@ def test_attention_spatial(F, S):
     ref = _attn_ref(qkv.float(), groups)
     out = eng.test_attn(False, qkv.cuda(), S).float().cpu()
     assert (out - ref).abs().max().item() < 8e-3
+
+
+def test_fp16_activations_saturate_instead_of_overflowing():
+    """activations are stored as IEEE fp16; a value beyond +-65504 must clamp (F2FP.SATFINITE), not turn
+    into inf (and NaN one softmax / LayerNorm later).  Bias of +-1e5 drives the qkv-style epilogue out of range."""
+    eng = _engine(27)
+    g = torch.Generator().manual_seed(3)
+    M, K, N = 256, 512, 1536
+    a = torch.randn(M, K, generator=g).half()
+    w = (torch.randn(N, K, generator=g) * 0.05).half()
+    bias = torch.zeros(N)
+    bias[::2], bias[1::2] = 1e5, -1e5
+    out = eng.test_gemm(0, a.cuda(), w.cuda(), bias.cuda()).float().cpu()
+    assert torch.isfinite(out).all()
+    assert (out[:, ::2] == 65504).all() and (out[:, 1::2] == -65504).all()
+    gel = eng.test_gemm(1, a.cuda(), w[:1024].cuda(), bias[:1024].cuda()).float().cpu()
+    assert torch.isfinite(gel).all() and (gel[:, ::2] == 65504).all() and (gel[:, 1::2].abs() < 1e-6).all()
