@@ -17,7 +17,6 @@
 #include "attn_temporal.cuh"
 #include "elementwise.cuh"
 #include "gemm_ln_pair.cuh"
-#include "gemm_ln_row.cuh"
 #include "gemm_tcgen05.cuh"
 
 using namespace d3dp;
@@ -223,23 +222,10 @@ static_assert(kSmemGemmQkv <= 232448 && kSmemGemmFc1 <= 232448, "exceeds the 227
 #define D3DP_LN_BSLOTS 2
 #define D3DP_LN_RING 1
 #endif
-#ifndef D3DP_LN_STAGES
-#define D3DP_LN_STAGES 2
-#endif
-constexpr int kLnA = D3DP_LN_ASLOTS, kLnB = D3DP_LN_BSLOTS, kLnStages = D3DP_LN_STAGES, kLnRing = D3DP_LN_RING;
+constexpr int kLnA = D3DP_LN_ASLOTS, kLnB = D3DP_LN_BSLOTS, kLnRing = D3DP_LN_RING;
 auto* const k_gemm_proj = gemm_ln_pair_kernel<EPI_RES_LN, kLnA, kLnB, kLnRing>;
 auto* const k_gemm_fc2 = gemm_ln_pair_kernel<EPI_RES_LN2, kLnA, kLnB, kLnRing>;
-#ifndef D3DP_LN_ROW
-#define D3DP_LN_ROW 0  // 1: gemm_ln_row.cuh (whole rows per CTA, cta_group::2) instead of gemm_ln_pair.cuh
-#endif
-#if D3DP_LN_ROW
-auto* const k_gemm_proj_row = gemm_ln_row_kernel<EPI_RES_LN, kLnStages, kLnRing>;
-auto* const k_gemm_fc2_row = gemm_ln_row_kernel<EPI_RES_LN2, kLnStages, kLnRing>;
-auto* const k_gemm_fc2_row_tpos = gemm_ln_row_kernel<EPI_RES_LN2, kLnStages, kLnRing, true>;
-constexpr int kSmemN512 = LnRowSmem<kLnStages, kLnRing>::TOTAL;
-#else
 constexpr int kSmemN512 = LnPairSmem<kLnA, kLnB, kLnRing>::TOTAL;
-#endif
 static_assert(kSmemN512 <= 232448, "LN pair kernel exceeds the 227 KB of shared memory per CTA");
 
 int ensure_attrs(d3dp_handle* h) {
@@ -247,14 +233,8 @@ int ensure_attrs(d3dp_handle* h) {
   int rc;
   if ((rc = set_smem_attr(h, k_gemm_qkv, kSmemGemmQkv))) return rc;
   if ((rc = set_smem_attr(h, k_gemm_fc1, kSmemGemmFc1))) return rc;
-#if D3DP_LN_ROW
-  if ((rc = set_smem_attr(h, k_gemm_proj_row, kSmemN512))) return rc;
-  if ((rc = set_smem_attr(h, k_gemm_fc2_row, kSmemN512))) return rc;
-  if ((rc = set_smem_attr(h, k_gemm_fc2_row_tpos, kSmemN512))) return rc;
-#else
   if ((rc = set_smem_attr(h, k_gemm_proj, kSmemN512))) return rc;
   if ((rc = set_smem_attr(h, k_gemm_fc2, kSmemN512))) return rc;
-#endif
   if ((rc = set_smem_attr(h, attn_temporal_kernel, ATT_SMEM_BYTES))) return rc;
   if ((rc = set_smem_attr(h, attn_temporal_long_kernel, ATTL_SMEM_BYTES))) return rc;
   if ((rc = set_smem_attr(h, attn_spatial_kernel, SP_SMEM_BYTES))) return rc;
@@ -293,18 +273,9 @@ int launch_gemm(d3dp_handle* h, int mode, const CUtensorMap& tmA, const CUtensor
     }
     case EPI_RES_LN:
     case EPI_RES_LN2: {
-#if D3DP_LN_ROW
-      // one CTA pair per 256-row tile; A box {64,128} (tmA as given), W box {64,128} (the caller passes tmap128)
-      const int pairs_m = (tiles_m + 1) / 2;
-      const int pairs = pairs_m < h->num_sms / 2 ? pairs_m : h->num_sms / 2;
-      if (mode == EPI_RES_LN) k_gemm_proj_row<<<2 * pairs, 352, kSmemN512, st>>>(tmA, tmB, tmC, tmO, p);
-      else if (p.tpos) k_gemm_fc2_row_tpos<<<2 * pairs, 352, kSmemN512, st>>>(tmA, tmB, tmC, tmO, p);
-      else k_gemm_fc2_row<<<2 * pairs, 352, kSmemN512, st>>>(tmA, tmB, tmC, tmO, p);
-#else
       const int pairs = tiles_m < h->num_sms / 2 ? tiles_m : h->num_sms / 2;  // one CTA pair (cluster) per M tile
       if (mode == EPI_RES_LN) k_gemm_proj<<<2 * pairs, LN_PAIR_THREADS, kSmemN512, st>>>(tmA64, tmB, tmC, tmO, p);
       else k_gemm_fc2<<<2 * pairs, LN_PAIR_THREADS, kSmemN512, st>>>(tmA64, tmB, tmC, tmO, p);
-#endif
       break;
     }
     default: return fail(h, D3DP_E_INVALID, "gemm: bad mode");
@@ -467,7 +438,7 @@ int run_denoiser(d3dp_handle* h, const Workspace& w, const DynArgs* dyn, const f
       p.ln_a_b = static_cast<const float*>(bw.n2b->dev);
       p.ln_a_eps = 1e-6f;
       p.row_scale = ds_attn; p.rs_mode = which == 0 ? 1 : 2;
-      if ((rc = launch_gemm(h, EPI_RES_LN, tm_o, D3DP_LN_ROW ? bw.projw->tmap128 : bw.projw->tmap, p, st))) return rc;
+      if ((rc = launch_gemm(h, EPI_RES_LN, tm_o, bw.projw->tmap, p, st))) return rc;
       // hidden = gelu(fc1(a16))
       p = GemmParams{};
       p.F = F; p.M = T; p.N = 1024; p.K = 512;
@@ -490,7 +461,7 @@ int run_denoiser(d3dp_handle* h, const Workspace& w, const DynArgs* dyn, const f
         p.ln_b_b = static_cast<const float*>(next->n1b->dev);
         p.ln_b_eps = 1e-6f;
       }
-      if ((rc = launch_gemm(h, EPI_RES_LN2, tm_h, D3DP_LN_ROW ? bw.fc2w->tmap128 : bw.fc2w->tmap, p, st))) return rc;
+      if ((rc = launch_gemm(h, EPI_RES_LN2, tm_h, bw.fc2w->tmap, p, st))) return rc;
     }
   }
   {
@@ -873,7 +844,7 @@ int d3dp_test_gemm(d3dp_handle* h, int32_t mode, const void* a16, const void* w1
   if ((rc = ensure_attrs(h))) return rc;
   CUtensorMap tmA, tmB;
   if ((rc = make_tmap(h, &tmA, a16, M, K, 128))) return rc;
-  if ((rc = make_tmap(h, &tmB, w16, N, K, (mode < 2 || D3DP_LN_ROW) ? 128 : 256))) return rc;
+  if ((rc = make_tmap(h, &tmB, w16, N, K, mode < 2 ? 128 : 256))) return rc;
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.bias = bias;
   p.out16 = static_cast<__half*>(out16);

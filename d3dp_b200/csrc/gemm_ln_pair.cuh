@@ -115,15 +115,12 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-#ifndef LNX_ABLATE
-#define LNX_ABLATE 0  // diagnostic builds: 1 = mainloop only (no epilogue work), 2 = epilogue only (no operands / MMA)
-#endif
   if (warp == 0) {
     // ------------------------------------------------------------------ operand TMA producer
     // The activation tile A streams from HBM (~2 us under load), the weights from L2: separate rings, so that A can
     // be ASLOTS k-blocks deep (16 KB each) without paying for as many 32 KB weight slots.
     // (warp 0: A, warp 11: B — independent threads, so the A stream runs ahead as far as ITS ring allows.)
-    if (lane == 0 && LNX_ABLATE != 2) {
+    if (lane == 0) {
       int sa = 0;
       uint32_t pha = 0;
       for (int tile = cluster_id; tile < tiles_m; tile += num_clusters) {
@@ -139,7 +136,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 11) {
     // ------------------------------------------------------------------ weight TMA producer
-    if (lane == 0 && LNX_ABLATE != 2) {
+    if (lane == 0) {
       int sb = 0;
       uint32_t phb = 0;
       for (int tile = cluster_id; tile < tiles_m; tile += num_clusters) {
@@ -153,7 +150,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && LNX_ABLATE != 2) {
+    if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(128, 256, 0, 0);
       int sa = 0, sb = 0, as = 0;
       uint32_t pha = 0, phb = 0, aph = 0;
@@ -182,16 +179,10 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------------ residual TMA loader (x tile, 32-col chunks)
-    if (lane == 0 && LNX_ABLATE != 1) {
+    if (lane == 0) {
       int slot = 0;
       uint32_t ph = 0;
       for (int tile = cluster_id; tile < tiles_m; tile += num_clusters) {
-#if defined(D3DP_LN_XPREFETCH) && D3DP_LN_XPREFETCH
-        // experiment: pull the NEXT tile's residual rows into L2 while this tile is worked on (the ring itself is
-        // only RING chunks deep, and x comes from HBM)
-        if (tile + num_clusters < tiles_m)
-          for (int c = 0; c < 8; ++c) tma_prefetch_l2_2d(&tmX, ncol0 + c * 32, (tile + num_clusters) * 128);
-#endif
         for (int c = 0; c < 4; ++c) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
@@ -286,18 +277,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       float rs = 1.0f;  // DropPath scale of this row's branch (x * 1.0f is exact: eval results do not change)
       if (p.row_scale && valid)
         rs = __ldg(p.row_scale + (p.rs_mode == 1 ? (grow / (17 * p.F)) * p.F + f : grow / p.F));
-#if LNX_ABLATE == 1
       mbar_wait(&tfull_bar[as], aph);
-      tc_fence_after();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      if (++as == 2) { as = 0; aph ^= 1; }
-      continue;
-#endif
-#if LNX_ABLATE != 2
-      mbar_wait(&tfull_bar[as], aph);
-#endif
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256 + lcol0;
 
@@ -343,10 +323,9 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       float t1 = 0.f, t2 = 0.f, py = 0.f;
       auto ln_a_chunk = [&](uint32_t (&v)[32], int c) {
         const int n = lcol0 + c * 32;
-#if defined(D3DP_TPOS_VEC) && D3DP_TPOS_VEC
-        // Experiment switch (default off, unmeasured): the thread's 32 Temporal_pos_embed values as four 256-bit
-        // loads instead of 32 scalar __ldg (row-per-thread: every warp load touches 32 rows = 32 L1 wavefronts;
-        // the S0 launch of fc2 measured 2.04 ms against 1.13-1.28 ms for the launches without the embedding).
+        // Temporal_pos_embed (block S0's fc2 only): the thread's 32 values as four 256-bit loads.  It is a
+        // row-per-thread access (every lane another row): 32 scalar loads per chunk touched 32 x 32 L1 wavefronts and
+        // made this launch 2.2 ms instead of 1.1 ms; the vector form brings it to 1.3 ms (profiles/r02_notes.md).
         uint32_t tp[32];
         if constexpr (EPI == EPI_RES_LN2) {
           if (p.tpos) {
@@ -355,16 +334,11 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int q = 0; q < 4; ++q) ldg256(src + 8 * q, *reinterpret_cast<uint32_t(*)[8]>(tp + 8 * q));
           }
         }
-#endif
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           float y = (__uint_as_float(v[i]) - mean) * rstd * sprm[256 + n + i] + sprm[512 + n + i];
           if constexpr (EPI == EPI_RES_LN2) {
-#if defined(D3DP_TPOS_VEC) && D3DP_TPOS_VEC
             if (p.tpos) y += __uint_as_float(tp[i]);
-#else
-            if (p.tpos) y += __ldg(p.tpos + static_cast<size_t>(f) * 512 + ncol0 + n + i);
-#endif
             if (c == 0 && i == 0) py = y;
             const float d = y - py;
             t1 += d;

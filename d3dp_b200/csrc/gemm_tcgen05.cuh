@@ -203,13 +203,6 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int m_blk = (ct / tiles_n) * 2 + rank, n_blk = ct % tiles_n;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
-#if defined(G2X_ABLATE) && G2X_ABLATE == 1  // diagnostic build: mainloop only (accumulators released unread)
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(tempty_leader0 + as * 8);
-      if (++as == 2) { as = 0; aph ^= 1; }
-      continue;
-#endif
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * GEMM_BN + col0;
       const int n0 = n_blk * GEMM_BN + col0;
 #pragma unroll 1

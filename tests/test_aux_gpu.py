@@ -386,3 +386,25 @@ def test_droppath_training_forward_matches_oracle():
         m.eval()
         e = m(x2d.cuda(), x_t.cuda(), t.cuda())
     assert mpjpe_distance(e, plain)[0] < 1e-3
+
+
+def test_workspace_contents_never_leak_into_results():
+    """The caller-owned workspace is carved into buffers that are aliased over time (the qkv activation and the MLP
+    hidden share one region) and written only by TMA stores, which compute-sanitizer's initcheck cannot see
+    (profiles/r02_sanitizer.md).  So the read-before-write check is done here: poison every byte of the workspace
+    with 0xFF (NaN in fp16 and fp32) and with 0x00 before a sampler call — the predictions must be finite and bit-equal."""
+    case = load_golden("f27_flip")
+    sd, x2d, x2d_flip, n0, ns = case_inputs(case)
+    m = build_model(27, case["H"], case["K"], sd)
+    eng = m.pose_estimator.engine()
+    outs = []
+    for fill in (0xFF, 0x00, 0xFF):
+        ws = eng.workspace(x2d.shape[0], case["H"], True)
+        ws.fill_(fill)
+        outs.append(m.ddim_sample_flip(x2d.cuda(), None, input_2d_flip=x2d_flip.cuda(), noise_init=n0, noise_steps=ns))
+        den = eng.workspace(x2d.shape[0], case["H"], False)
+        den.fill_(fill)
+        outs.append(m.pose_estimator(x2d.cuda(), n0.clamp(-1.1, 1.1).cuda(), case["denoise_t"].cuda()))
+    assert all(torch.isfinite(o).all() for o in outs)
+    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[0], outs[4])
+    assert torch.equal(outs[1], outs[3]) and torch.equal(outs[1], outs[5])
