@@ -217,10 +217,14 @@ constexpr int kSmemGemmQkv = Gemm2SmSmem<6, 1, false>::TOTAL;
 auto* const k_gemm_fc1 = gemm_2sm_kernel<EPI_BIAS_GELU_F16, 4, 2, true>;
 constexpr int kSmemGemmFc1 = Gemm2SmSmem<4, 2, true>::TOTAL;
 static_assert(kSmemGemmQkv <= 232448 && kSmemGemmFc1 <= 232448, "exceeds the 227 KB of shared memory per CTA");
+// LayerNorm GEMMs: A ring 3 x 16 KB (streams from HBM), weight ring 2 x 32 KB (L2 hits), residual ring 2 x 16 KB per
+// epilogue group — the best of the configurations that fit 227 KB, at kernel level and inside the sampler
+// (profiles/r02_ab_ln2_*.log: proj 0.795 -> 0.714 ms, fc2 1.235 -> 1.18 ms, sampler call 76.9 -> 74.5 ms against the
+// round-1 layout of 2 uniform 48 KB stages).  Overridable for A/B builds.
 #ifndef D3DP_LN_ASLOTS
-#define D3DP_LN_ASLOTS 4
+#define D3DP_LN_ASLOTS 3
 #define D3DP_LN_BSLOTS 2
-#define D3DP_LN_RING 1
+#define D3DP_LN_RING 2
 #endif
 constexpr int kLnA = D3DP_LN_ASLOTS, kLnB = D3DP_LN_BSLOTS, kLnRing = D3DP_LN_RING;
 auto* const k_gemm_proj = gemm_ln_pair_kernel<EPI_RES_LN, kLnA, kLnB, kLnRing>;

@@ -92,7 +92,7 @@ def one():
         from d3dp_b200.synthetic import (H36M_JOINTS_LEFT as JL, H36M_JOINTS_RIGHT as JR, flip_2d,
                                          synthetic_pose_estimator_state)
         from d3dp_b200.synthetic import make_args
-        F, B, H, K = 243, 2, 10, 2
+        F, B, H, K = 243, *[int(v) for v in os.environ.get("AB_SAMPLER", "2,10,2").split(",")]  # AB_SAMPLER="B,H,K"
         model = D3DP(make_args(F), JL, JR, is_train=False, num_proposals=H, sampling_timesteps=K)
         model.pose_estimator.load_state_dict(synthetic_pose_estimator_state(F, seed=0), strict=True)
         model = model.cuda().eval()
