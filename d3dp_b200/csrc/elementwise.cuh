@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int BH = p.B * p.H;
-  const long long T = static_cast<long long>(p.n_streams) * kJ * p.F;
+  const int T = p.n_streams * kJ * p.F;  // rows: fits 32 bits by far (7 KB of workspace per row); 64-bit div/mod per
+                                         // token cost more than the token's arithmetic
   const float* x2d_plain = p.dyn ? p.dyn->x2d : p.x2d;
   const float* x2d_flip = p.dyn ? p.dyn->x2d_flip : p.x2d_flip;
   const int c0 = lane * 16;  // this lane's channels [c0, c0 + 16)
@@ -143,11 +144,11 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
     lg[i] = p.ln_g[c0 + i];
     lb[i] = p.ln_b[c0 + i];
   }
-  for (long long row = warp; row < T; row += nwarps) {
-    const int f = static_cast<int>(row % p.F);
-    const long long sj = row / p.F;
-    const int j = static_cast<int>(sj % kJ);
-    const int s = static_cast<int>(sj / kJ);
+  for (int row = warp; row < T; row += nwarps) {
+    const int sj = row / p.F;
+    const int f = row - sj * p.F;
+    const int s = sj / kJ;
+    const int j = sj - s * kJ;
     const bool flip = s >= BH;
     const int bh = flip ? s - BH : s;
     const int b = bh / p.H;
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
 #pragma unroll
     for (int d = 16; d; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
     const float rstd = rsqrtf(sq * (1.0f / kC) + p.ln_eps);
-    float4* xr = reinterpret_cast<float4*>(p.x + row * kC + c0);
+    float4* xr = reinterpret_cast<float4*>(p.x + static_cast<size_t>(row) * kC + c0);
 #pragma unroll
     for (int q = 0; q < 4; ++q) xr[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     uint32_t h[8];
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
     for (int i = 0; i < 8; ++i)
       h[i] = pack_half2((v[2 * i] - mean) * rstd * lg[2 * i] + lb[2 * i],
                         (v[2 * i + 1] - mean) * rstd * lg[2 * i + 1] + lb[2 * i + 1]);
-    uint4* ar = reinterpret_cast<uint4*>(p.a16 + row * kC + c0);
+    uint4* ar = reinterpret_cast<uint4*>(p.a16 + static_cast<size_t>(row) * kC + c0);
     ar[0] = make_uint4(h[0], h[1], h[2], h[3]);
     ar[1] = make_uint4(h[4], h[5], h[6], h[7]);
   }
@@ -217,9 +218,9 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ x, 
                                                    float* __restrict__ out, int n_streams, int F) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const long long T = static_cast<long long>(n_streams) * kJ * F;
-  for (long long row = warp; row < T; row += nwarps) {
-    const float* xr = x + row * kC;
+  const int T = n_streams * kJ * F;
+  for (int row = warp; row < T; row += nwarps) {
+    const float* xr = x + static_cast<size_t>(row) * kC;
     float v[16];
     float sum = 0.f;
 #pragma unroll
@@ -252,11 +253,11 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ x, 
       o2 += __shfl_xor_sync(0xffffffffu, o2, d);
     }
     if (lane == 0) {
-      const int f = static_cast<int>(row % F);
-      const long long sj = row / F;
-      const int j = static_cast<int>(sj % kJ);
-      const long long s = sj / kJ;
-      float* o = out + ((s * F + f) * kJ + j) * 3;
+      const int sj = row / F;
+      const int f = row - sj * F;
+      const int s = sj / kJ;
+      const int j = sj - s * kJ;
+      float* o = out + ((static_cast<size_t>(s) * F + f) * kJ + j) * 3;
       o[0] = o0 + b_h[0];
       o[1] = o1 + b_h[1];
       o[2] = o2 + b_h[2];

@@ -42,7 +42,7 @@ def main():
         traj, cam = (t.to(dev) for t in synthetic_camera(B, F))
         for H in (1, 5, 20, 80):
             for K in (1, 5, 10):
-                if quick and (H, K) not in ((1, 1), (1, 10), (20, 10)):
+                if quick and (H, K) not in ((1, 1), (1, 10), (5, 5), (20, 10), (80, 10)):
                     continue
                 model = D3DP(make_args(F), JL, JR, is_train=False, num_proposals=H, sampling_timesteps=K)
                 model.pose_estimator.load_state_dict(sd, strict=True)
