@@ -5,6 +5,8 @@
 // mma.sync.m16n8k16 path with a shuffle softmax: Q (padded to 32 rows) x K^T (padded to 24 keys), softmax in
 // registers, P (32x32) x V (32 keys x 64).  Token order is [S, J, F]: the 17 rows of a spatial sequence are F rows
 // apart, each a contiguous 3 KB fp16 qkv row, so the CTA gathers 17 rows with cp.async and every warp works from smem.
+// All MMA fragments come from ldmatrix (Q and K plain, V transposed); the padding rows of the 32 x 24 / 32 x 32 tiles
+// do not exist in shared memory: their ldmatrix row pointers aim at one 16-byte block of zeros.
 // It is an HBM-bound kernel (4 KB/token in+out); the MMA shape padding is irrelevant to its speed.
 #pragma once
 #include "ptx.cuh"
@@ -22,7 +24,17 @@ struct AttnSParams {
 constexpr int SP_J = 17;
 constexpr int SP_ROW_HALFS = 1536 + 8;  // +16 B pad: consecutive joints land 4 banks apart -> conflict-free fragments
 constexpr int SP_BUF_BYTES = SP_J * SP_ROW_HALFS * 2;
-constexpr int SP_SMEM_BYTES = 2 * SP_BUF_BYTES;  // double-buffered: the next (stream, frame) streams in during compute
+constexpr int SP_ZERO_OFFSET = 2 * SP_BUF_BYTES;  // 16 zero bytes: the "row" every padding row of a fragment points to
+constexpr int SP_SMEM_BYTES = SP_ZERO_OFFSET + 16;  // double-buffered: the next (stream, frame) streams in during compute
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
 
 __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -50,6 +62,8 @@ __global__ void __launch_bounds__(256) attn_spatial_kernel(const AttnSParams p) 
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  if (threadIdx.x < 4) reinterpret_cast<uint32_t*>(sp_smem + SP_ZERO_OFFSET)[threadIdx.x] = 0u;
+  const uint32_t zero_addr = smem_u32(sp_smem + SP_ZERO_OFFSET);
   int buf = 0;
   if (blockIdx.x < num_items) prefetch(blockIdx.x, 0);
   for (int item = blockIdx.x; item < num_items; item += gridDim.x, buf ^= 1) {
@@ -68,8 +82,9 @@ __global__ void __launch_bounds__(256) attn_spatial_kernel(const AttnSParams p) 
     __half* Q = cur + h * 64;
     const __half* K = cur + 512 + h * 64;
     const __half* V = cur + 1024 + h * 64;
-    auto ld32 = [&](const __half* base, int row, int col) -> uint32_t {
-      return row < SP_J ? *reinterpret_cast<const uint32_t*>(base + row * SP_ROW_HALFS + col) : 0u;
+    // shared-memory address of the 16-byte row piece (row, col..col+7) of a [17 x 64] head slice, or the zero block
+    auto row_addr = [&](const __half* base, int row, int col) -> uint32_t {
+      return row < SP_J ? smem_u32(base + row * SP_ROW_HALFS + col) : zero_addr;
     };
 
     // ---- S = Q K^T : 2 m-tiles (rows 0-15, 16-31) x 3 n-tiles (keys 0-7, 8-15, 16-23), k = 64 in 4 steps
@@ -81,22 +96,21 @@ __global__ void __launch_bounds__(256) attn_spatial_kernel(const AttnSParams p) 
 #pragma unroll
         for (int i = 0; i < 4; ++i) sacc[mt][nt][i] = 0.f;
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const int k0 = ks * 16 + 2 * t;
-      uint32_t a[2][4];
+    for (int kp = 0; kp < 2; ++kp) {  // pairs of k-steps: one ldmatrix.x4 of K covers k-steps 2kp and 2kp+1
+      uint32_t bk[3][4];              // per n-tile: {b0,b1} of k-step 2kp, {b0,b1} of k-step 2kp+1
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        a[mt][0] = ld32(Q, mt * 16 + g, k0);
-        a[mt][1] = ld32(Q, mt * 16 + g + 8, k0);
-        a[mt][2] = ld32(Q, mt * 16 + g, k0 + 8);
-        a[mt][3] = ld32(Q, mt * 16 + g + 8, k0 + 8);
-      }
+      for (int nt = 0; nt < 3; ++nt)  // matrices: (k lo, ks 2kp) (k hi, ks 2kp) (k lo, ks 2kp+1) (k hi, ks 2kp+1); rows = keys
+        ldmatrix_x4(bk[nt], row_addr(K, nt * 8 + (lane & 7), kp * 32 + (lane >> 3) * 8));
 #pragma unroll
-      for (int nt = 0; nt < 3; ++nt) {
-        const uint32_t b0 = ld32(K, nt * 8 + g, k0);
-        const uint32_t b1 = ld32(K, nt * 8 + g, k0 + 8);
+      for (int kk = 0; kk < 2; ++kk) {
+        const int ks = kp * 2 + kk;
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) mma_16816(sacc[mt][nt], a[mt], b0, b1);
+        for (int mt = 0; mt < 2; ++mt) {
+          uint32_t a[4];  // matrices: (rows 0-7, k lo) (rows 8-15, k lo) (rows 0-7, k hi) (rows 8-15, k hi)
+          ldmatrix_x4(a, row_addr(Q, mt * 16 + (lane & 15), ks * 16 + (lane >> 4) * 8));
+#pragma unroll
+          for (int nt = 0; nt < 3; ++nt) mma_16816(sacc[mt][nt], a, bk[nt][2 * kk], bk[nt][2 * kk + 1]);
+        }
       }
     }
     // ---- softmax over the 17 valid keys; C fragment: c0,c1 -> (row g, keys nt*8+2t, +1); c2,c3 -> row g+8
@@ -150,23 +164,20 @@ __global__ void __launch_bounds__(256) attn_spatial_kernel(const AttnSParams p) 
       for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
         for (int i = 0; i < 4; ++i) oacc[mt][nt][i] = 0.f;
-    auto ldv = [&](int key, int col) -> uint32_t {  // two keys (key, key+1) of one column packed lo/hi
-      const uint16_t lo = key < SP_J ? *reinterpret_cast<const uint16_t*>(V + key * SP_ROW_HALFS + col) : 0;
-      const uint16_t hi = key + 1 < SP_J ? *reinterpret_cast<const uint16_t*>(V + (key + 1) * SP_ROW_HALFS + col) : 0;
-      return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
-    };
+    // V fragments with ldmatrix.trans: matrices (keys lo, n-tile 2np) (keys hi, 2np) (keys lo, 2np+1) (keys hi, 2np+1)
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const int col = nt * 8 + g;
-      {  // k-step 0: keys 0..15
-        const uint32_t b0 = ldv(2 * t, col), b1 = ldv(2 * t + 8, col);
-        mma_16816(oacc[0][nt], pa[0][0], b0, b1);
-        mma_16816(oacc[1][nt], pa[1][0], b0, b1);
-      }
-      {  // k-step 1: keys 16..31 (only key 16 is real)
-        const uint32_t b0 = ldv(16 + 2 * t, col);
-        mma_16816(oacc[0][nt], pa[0][1], b0, 0u);
-        mma_16816(oacc[1][nt], pa[1][1], b0, 0u);
+    for (int np = 0; np < 4; ++np) {
+      const int col = (np * 2 + (lane >> 4)) * 8;
+      uint32_t v0[4], v1[4];
+      ldmatrix_x4_trans(v0, row_addr(V, (lane & 7) + ((lane >> 3) & 1) * 8, col));       // k-step 0: keys 0..15
+      ldmatrix_x4_trans(v1, row_addr(V, 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col));  // k-step 1: key 16 (+ zeros)
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int nt = np * 2 + h2;
+        mma_16816(oacc[0][nt], pa[0][0], v0[2 * h2], v0[2 * h2 + 1]);
+        mma_16816(oacc[1][nt], pa[1][0], v0[2 * h2], v0[2 * h2 + 1]);
+        mma_16816(oacc[0][nt], pa[0][1], v1[2 * h2], v1[2 * h2 + 1]);
+        mma_16816(oacc[1][nt], pa[1][1], v1[2 * h2], v1[2 * h2 + 1]);
       }
     }
     // ---- store: stage the head's 17 x 64 outputs in the warp's own (now dead) Q slice, then write 16 B per lane

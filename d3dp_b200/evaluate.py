@@ -16,6 +16,8 @@ What differs from the reference's loop, and why:
     batch i's sampler graph is launched on the compute stream and run underneath it; the compute stream waits on
     a per-batch event only.  The reference does all of this on the host between two sampler calls (main.py:646-696).
 """
+import contextlib
+
 import torch
 
 from . import clips as C
@@ -32,20 +34,23 @@ def evaluate_sequences(model, sequences, kps_left, kps_right, batch_size, root_j
     `sampler(x2d, x2d_flip, batch_index)` may replace the model call (tests)."""
     eng = model.pose_estimator.engine()
     dev, F = eng.device, model.frames
-    main = torch.cuda.current_stream(dev)
-    prep = torch.cuda.Stream(device=dev) if overlap else main
-    prep.wait_stream(main)  # inputs that already live on the device were produced on the compute stream
+    cuda = dev.type == "cuda"  # (the host-logic tests drive this function with a CPU stand-in engine: no streams there)
+    main = torch.cuda.current_stream(dev) if cuda else None
+    prep = torch.cuda.Stream(device=dev) if (cuda and overlap) else main
+    on_prep = (lambda: torch.cuda.stream(prep)) if cuda else contextlib.nullcontext
+    if cuda:
+        prep.wait_stream(main)  # inputs that already live on the device were produced on the compute stream
 
     def upload(t):  # host tensors go up asynchronously from pinned memory, on the preparation stream
-        if t.device.type == "cpu":
+        if cuda and t.device.type == "cpu":
             t = t.to(torch.float32).pin_memory()
         return t.to(dev, torch.float32, non_blocking=True)
-    with torch.cuda.stream(prep):
+    with on_prep():
         prepared = _cut_all(sequences, upload, F, kps_left, kps_right, batch_size, root_joint, dev)
     x2d_c, flip_c, gt_c, traj_c, cam_c, group, nframes, n_groups = prepared
     n_clips = x2d_c.shape[0]
 
-    with torch.cuda.stream(prep):
+    with on_prep():
         if packed:
             batch_list = [torch.arange(s.start, s.stop, device=dev) for s in C.batches(n_clips, batch_size)]
         else:
@@ -55,13 +60,16 @@ def evaluate_sequences(model, sequences, kps_left, kps_right, batch_size, root_j
         """Gather the inputs of batch bi on the preparation stream; returns them with the event the compute stream
         waits on.  Called one batch ahead, i.e. before the previous batch's sampler has been launched."""
         idx = batch_list[bi]
-        with torch.cuda.stream(prep):
+        with on_prep():
             items = [x2d_c[idx].contiguous(), flip_c[idx].contiguous(), gt_c[idx], traj_c[idx], cam_c[idx].contiguous(),
                      group[idx]]
-            ev = torch.cuda.Event()
-            ev.record(prep)
-        for t in items:
-            t.record_stream(main)
+            ev = None
+            if cuda:
+                ev = torch.cuda.Event()
+                ev.record(prep)
+        if cuda:
+            for t in items:
+                t.record_stream(main)
         return items, ev
 
     K = H = None
@@ -71,7 +79,8 @@ def evaluate_sequences(model, sequences, kps_left, kps_right, batch_size, root_j
         (xb, fb, gtb, trajb, camb, grp), ev = nxt
         if bi + 1 < len(batch_list):
             nxt = prepare(bi + 1)
-        main.wait_event(ev)
+        if cuda:
+            main.wait_event(ev)
         if sampler is not None:
             preds = sampler(xb, fb, bi)
         else:
@@ -95,7 +104,8 @@ def evaluate_sequences(model, sequences, kps_left, kps_right, batch_size, root_j
         if return_poses:
             poses["jagg_pose"].append(m["jagg_pose"])
             poses["pagg_pose"].append(m["pagg_pose"])
-    main.wait_stream(prep)
+    if cuda:
+        main.wait_stream(prep)
     return _finish(acc, poses, group, batch_list, nframes, n_groups, n_clips, F, K, H, protocol2, return_poses, dev)
 
 
