@@ -90,6 +90,12 @@ class Engine:
     def _f32(self, t):
         return t.detach().to(self.device, torch.float32).contiguous()
 
+    @staticmethod
+    def _expect(t, shape, what):
+        """The C ABI takes raw pointers: a tensor of the wrong shape would be read out of bounds, so refuse it here."""
+        if t is not None and tuple(t.shape) != tuple(shape):
+            raise D3dpError(f"{what}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+
     # ------------------------------------------------------------------ entry points
     def drop_scale_numel(self, n_streams):
         """Elements of the packed DropPath factor buffer d3dp_denoise takes (include/d3dp_b200.h)."""
@@ -99,6 +105,9 @@ class Engine:
         x2d, x_t = self._f32(x2d), self._f32(x_t)
         t = t.detach().to(self.device, torch.int64).contiguous()
         B, H = x_t.shape[0], x_t.shape[1]
+        self._expect(x2d, (B, self.frames, 17, 2), "x_2d")
+        self._expect(x_t, (B, H, self.frames, 17, 3), "x_3d")
+        self._expect(t, (B,), "t")
         if drop_scale is not None:
             drop_scale = self._f32(drop_scale)
             assert drop_scale.numel() == self.drop_scale_numel(B * H)
@@ -117,6 +126,10 @@ class Engine:
         noise_steps = None if noise_steps is None else self._f32(noise_steps)
         B = x2d.shape[0]
         H_total = H if H_total is None else H_total
+        self._expect(x2d, (B, self.frames, 17, 2), "inputs_2d")
+        self._expect(x2d_flip, (B, self.frames, 17, 2), "input_2d_flip")
+        self._expect(noise_init, (B, H, self.frames, 17, 3), "noise_init")
+        self._expect(noise_steps, (max(K - 1, 0), B, H, self.frames, 17, 3), "noise_steps")
         preds = torch.empty(B, K, H, self.frames, 17, 3, dtype=torch.float32, device=self.device)
         ws = self.workspace(B, H, x2d_flip is not None)
         ts = None
@@ -149,6 +162,9 @@ class Engine:
         else:
             assert shards == 1
             B, K, H = preds.shape[0], preds.shape[1], preds.shape[2]
+        if preds.dim() not in (6, 7) or tuple(preds.shape[-3:]) != (self.frames, 17, 3) or traj.numel() != B * self.frames * 3:
+            raise D3dpError(f"jpma: preds {tuple(preds.shape)} / traj {tuple(traj.shape)} do not match F={self.frames}")
+        self._expect(x2d, (B, self.frames, 17, 2), "jpma x2d")
         traj = traj.reshape(B, self.frames, 3)
         if cam.dim() == 1:
             cam = cam[None].expand(B, 9).contiguous()
@@ -166,6 +182,9 @@ class Engine:
         """JPMA plus the ground-truth-dependent outputs (per-hypothesis 3-D errors, J-Best pose)."""
         preds, traj, cam, x2d, gt = (self._f32(t) for t in (preds, traj, cam, x2d, gt))
         B, K, H = preds.shape[0], preds.shape[1], preds.shape[2]
+        self._expect(preds, (B, K, H, self.frames, 17, 3), "jpma_gt preds")
+        self._expect(x2d, (B, self.frames, 17, 2), "jpma_gt x2d")
+        self._expect(gt, (B, self.frames, 17, 3), "jpma_gt gt")
         traj = traj.reshape(B, self.frames, 3)
         if cam.dim() == 1:
             cam = cam[None].expand(B, 9).contiguous()

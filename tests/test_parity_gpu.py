@@ -90,3 +90,40 @@ def test_sampler_stays_finite_and_close_with_large_weights():
     mean, mx = mpjpe_distance(out, ref)
     print(f"\n[parity] x4 qkv/fc1 weights: mean {mean:.3e} max {mx:.3e}")
     assert mean <= MEAN_TOL and mx <= MAX_TOL
+
+
+@pytest.mark.parametrize("F,B,H,K,flip", [(384, 1, 1, 1, True), (1, 3, 2, 2, True), (2, 1, 1, 2, False), (129, 1, 1, 1, True)])
+def test_sampler_edge_sizes_match_oracle(F, B, H, K, flip):
+    """Edge cases of the path: the largest supported clip (F = 384, three query tiles in the long temporal kernel), a
+    single frame (temporal attention over one key), two frames without flip, and one frame past a 128-row query tile."""
+    from d3dp_b200.synthetic import synthetic_inputs, synthetic_pose_estimator_state
+    from oracle import d3dp_oracle as orc
+    sd = synthetic_pose_estimator_state(F, seed=13)
+    x2d, x2d_flip, n0, ns = synthetic_inputs(B, H, K, F, seed=F + 1, noise_seed=F + 2)
+    with torch.no_grad():
+        ref = orc.ddim_sample(sd, x2d, x2d_flip if flip else None, H, K, n0, ns, JL, JR)
+    model = build_model(F, H, K, sd, flip=flip)
+    if flip:
+        out = model.ddim_sample_flip(x2d.cuda(), None, input_2d_flip=x2d_flip.cuda(), noise_init=n0, noise_steps=ns)
+    else:
+        out = torch.stack(model.ddim_sample(x2d.cuda(), None, noise_init=n0, noise_steps=ns), dim=1)
+    mean, mx = mpjpe_distance(out, ref)
+    print(f"\n[parity] edge F={F} B={B} H={H} K={K} flip={flip}: mean {mean:.3e} max {mx:.3e}")
+    assert out.shape == ref.shape and mean <= MEAN_TOL and mx <= MAX_TOL
+
+
+def test_invalid_calls_fail_loudly():
+    """Empty batches, a wrong frame count and a shard range outside H_total are refused with an error, not computed."""
+    from d3dp_b200._lib import D3dpError
+    case = load_golden("f27_flip")
+    sd, x2d, x2d_flip, n0, ns = case_inputs(case)
+    m = build_model(27, 2, 2, sd)
+    with pytest.raises(D3dpError):
+        m.ddim_sample_flip(x2d[:0].cuda(), None, input_2d_flip=x2d_flip[:0].cuda())
+    with pytest.raises(D3dpError):
+        m.ddim_sample_flip(x2d.cuda(), None, input_2d_flip=x2d_flip.cuda(), seed=1, h_offset=-1, H_total=4)
+    with pytest.raises(D3dpError):
+        m.ddim_sample_flip(x2d.cuda(), None, input_2d_flip=x2d_flip.cuda(), seed=1, h_offset=3, H_total=4)
+    with pytest.raises((D3dpError, AssertionError, RuntimeError)):
+        m.pose_estimator.engine().jpma(torch.zeros(2, 2, 2, 26, 17, 3), torch.zeros(2, 27, 1, 3), torch.zeros(2, 9),
+                                       torch.zeros(2, 27, 17, 2))
