@@ -361,6 +361,10 @@ Workspace carve(const d3dp_handle* h, void* base, int B, int H, int n_streams) {
   return w;
 }
 
+// The per-call argument block travels as a kernel PARAMETER (copied at launch, fully asynchronous for the host) —
+// a cudaMemcpyAsync from pageable memory may synchronise the stream before it stages the source.
+__global__ void set_dyn_kernel(DynArgs* dst, const DynArgs v) { *dst = v; }
+
 __global__ void fill_t_kernel(long long* t, int B, long long v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) t[i] = v;
@@ -735,9 +739,10 @@ int d3dp_ddim_sample(d3dp_handle* h, const float* x2d, const float* x2d_flip, co
     if (times[k] < 0 || times[k] >= h->cfg.num_timesteps || times[k + 1] >= times[k] || (k + 1 < K && times[k + 1] < 0))
       return fail(h, D3DP_E_INVALID, "ddim_sample: bad timestep list");
 
-  // everything that changes from call to call goes through the DynArgs block (one small H2D copy, staged before return)
+  // everything that changes from call to call goes through the DynArgs block (one single-thread launch ahead of the graph)
   const DynArgs dyn{x2d, x2d_flip, noise_init, noise_steps, preds, static_cast<unsigned long long>(seed)};
-  CK(cudaMemcpyAsync(w.dyn, &dyn, sizeof(DynArgs), cudaMemcpyHostToDevice, st));
+  set_dyn_kernel<<<1, 1, 0, st>>>(w.dyn, dyn);
+  CK(cudaGetLastError());
 
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (st) cudaStreamIsCapturing(st, &cap);

@@ -103,8 +103,9 @@ int d3dp_denoise(d3dp_handle* h, const float* x2d, const float* x_t, const int64
  * descending ints ending in -1, or NULL to use d3dp_time_list.
  * The loop of common/diffusionpose.py:229-254 is captured once per (B, H, K, flip, h_offset, H_total, timesteps,
  * workspace) into a CUDA graph and replayed on `stream`; caller-owned pointers and the seed reach the kernels through
- * a small device-side argument block, so they may change freely between calls.  (Environment D3DP_GRAPH=0 at
- * d3dp_create, or a `stream` that is itself being captured: plain kernel-by-kernel launches.) */
+ * a small device-side argument block (written by a one-thread kernel ahead of the graph: the call never blocks
+ * the host), so they may change freely between calls.  (Environment D3DP_GRAPH=0 at d3dp_create, or a `stream` that is
+ * itself being captured: plain kernel-by-kernel launches, which are then captured into the caller's graph.) */
 int d3dp_ddim_sample(d3dp_handle* h, const float* x2d, const float* x2d_flip, const float* noise_init,
                      const float* noise_steps, uint64_t seed, int32_t h_offset, int32_t H_total,
                      const int32_t* timesteps_host, float* preds, int32_t B, int32_t H, int32_t K, void* workspace,
