@@ -122,10 +122,11 @@ struct EmbedParams {
   int perm[kJ];           // joint permutation of the flip
 };
 
-// A lane owns 16 CONSECUTIVE channels, so a token's 2 KB of x and 1 KB of a16 leave as 4 + 2 128-bit stores per lane
-// (the first version's mapping channel = i*32 + lane needed 16 32-bit + 16 16-bit stores: 0.8 ms for 2 GB; this one
-// took 0.9 ms off a 38 ms sampler call in the round-2 A/B).  The lane's 16 x 5 weights + bias + LayerNorm affine stay
-// in registers for all its tokens.
+// A lane owns the four channels 4*lane .. 4*lane+3 of each 128-channel quarter of the row, so every store instruction
+// of the warp writes one contiguous 512-byte (x, 128-bit per lane) or 256-byte (a16, 64-bit per lane) run: 4 + 4
+// fully coalesced stores per token.  (Round 1's mapping channel = i*32 + lane needed 16 + 16 scalar stores; 16
+// CONSECUTIVE channels per lane gives 128-bit stores that are 64 bytes apart across lanes, i.e. half-filled sectors.)
+// The lane's 16 x 5 weights + bias + LayerNorm affine stay in registers for all its tokens.
 __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -134,15 +135,16 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
                                          // token cost more than the token's arithmetic
   const float* x2d_plain = p.dyn ? p.dyn->x2d : p.x2d;
   const float* x2d_flip = p.dyn ? p.dyn->x2d_flip : p.x2d_flip;
-  const int c0 = lane * 16;  // this lane's channels [c0, c0 + 16)
+  const int c0 = lane * 4;  // this lane's channels: 128 q + c0 + e, q = 0..3, e = 0..3  (register index i = 4 q + e)
   float we[16][5], be[16], lg[16], lb[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
+    const int c = 128 * (i >> 2) + c0 + (i & 3);
 #pragma unroll
-    for (int k = 0; k < 5; ++k) we[i][k] = p.w_e[(c0 + i) * 5 + k];
-    be[i] = p.b_e[c0 + i];
-    lg[i] = p.ln_g[c0 + i];
-    lb[i] = p.ln_b[c0 + i];
+    for (int k = 0; k < 5; ++k) we[i][k] = p.w_e[c * 5 + k];
+    be[i] = p.b_e[c];
+    lg[i] = p.ln_g[c];
+    lb[i] = p.ln_b[c];
   }
   for (int row = warp; row < T; row += nwarps) {
     const int sj = row / p.F;
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
     float sum = 0.f;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float4 s4 = __ldg(sp + q), t4 = __ldg(ta + q);
+      const float4 s4 = __ldg(sp + 32 * q), t4 = __ldg(ta + 32 * q);  // quarter q: 128 floats = 32 float4 further on
       const float add[4] = {s4.x + t4.x, s4.y + t4.y, s4.z + t4.z, s4.w + t4.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -197,15 +199,15 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
     const float rstd = rsqrtf(sq * (1.0f / kC) + p.ln_eps);
     float4* xr = reinterpret_cast<float4*>(p.x + static_cast<size_t>(row) * kC + c0);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) xr[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    for (int q = 0; q < 4; ++q) xr[32 * q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     uint32_t h[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       h[i] = pack_half2((v[2 * i] - mean) * rstd * lg[2 * i] + lb[2 * i],
                         (v[2 * i + 1] - mean) * rstd * lg[2 * i + 1] + lb[2 * i + 1]);
-    uint4* ar = reinterpret_cast<uint4*>(p.a16 + static_cast<size_t>(row) * kC + c0);
-    ar[0] = make_uint4(h[0], h[1], h[2], h[3]);
-    ar[1] = make_uint4(h[4], h[5], h[6], h[7]);
+    uint2* ar = reinterpret_cast<uint2*>(p.a16 + static_cast<size_t>(row) * kC + c0);  // 4 halfs per quarter
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ar[32 * q] = make_uint2(h[2 * q], h[2 * q + 1]);  // quarter q: 128 halfs = 32 uint2 on
   }
 }
 
@@ -219,14 +221,29 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ x, 
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int T = n_streams * kJ * F;
+  // lane owns channels 128 q + 4 lane + e (q, e = 0..3): four coalesced 128-bit loads per row; its slice of the
+  // LayerNorm affine and of the 3 x 512 head weights stays in registers for all its rows
+  const int c0 = lane * 4;
+  float g[16], bt[16], w0[16], w1[16], w2[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = 128 * (i >> 2) + c0 + (i & 3);
+    g[i] = ln_g[c];
+    bt[i] = ln_b[c];
+    w0[i] = w_h[c];
+    w1[i] = w_h[kC + c];
+    w2[i] = w_h[2 * kC + c];
+  }
+  const float b0 = b_h[0], b1 = b_h[1], b2 = b_h[2];
   for (int row = warp; row < T; row += nwarps) {
-    const float* xr = x + static_cast<size_t>(row) * kC;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * kC + c0);
     float v[16];
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      v[i] = xr[i * 32 + lane];
-      sum += v[i];
+    for (int q = 0; q < 4; ++q) {
+      const float4 t = __ldg(xr + 32 * q);
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+      sum += (t.x + t.y) + (t.z + t.w);
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
@@ -240,11 +257,10 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ x, 
     float o0 = 0.f, o1 = 0.f, o2 = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const int c = i * 32 + lane;
-      const float y = (v[i] - mean) * rstd * ln_g[c] + ln_b[c];
-      o0 += y * w_h[c];
-      o1 += y * w_h[kC + c];
-      o2 += y * w_h[2 * kC + c];
+      const float y = (v[i] - mean) * rstd * g[i] + bt[i];
+      o0 += y * w0[i];
+      o1 += y * w1[i];
+      o2 += y * w2[i];
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
@@ -258,9 +274,9 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ x, 
       const int s = sj / kJ;
       const int j = sj - s * kJ;
       float* o = out + ((static_cast<size_t>(s) * F + f) * kJ + j) * 3;
-      o[0] = o0 + b_h[0];
-      o[1] = o1 + b_h[1];
-      o[2] = o2 + b_h[2];
+      o[0] = o0 + b0;
+      o[1] = o1 + b1;
+      o[2] = o2 + b2;
     }
   }
 }
