@@ -462,7 +462,8 @@ def run_ours(args, rank, world, local_rank):
     dom_flops = {"gemm_qkv": 2.0 * T * 1536 * 512, "gemm_fc1_gelu": 2.0 * T * 1024 * 512,
                  "gemm_proj_res_ln": 2.0 * T * 512 * 512, "gemm_fc2_res_ln2": 2.0 * T * 512 * 1024,
                  "attn_temporal": 4.0 * F * C * T, "attn_spatial": 4.0 * J * C * T}[dom]
-    launches_per_call = 1 + K * (3 + 16 * 5 + 1 + 1) + 1  # init_img; per step fill_t,time_mlp,embed + 16x5 + head + ddim; jpma
+    # set_dyn, init_img, K x fill_t, one time_mlp for all steps; per step embed + 16 blocks x 5 + head + ddim; jpma
+    launches_per_call = 3 + K + K * (1 + 16 * 5 + 1 + 1) + 1
     cpu_line = None
     if world == 1 and not args.no_cpu_baseline:
         v, t_s, cores = cpu_reference_sample(repeats=4, warmup=1)
@@ -483,7 +484,7 @@ def run_ours(args, rank, world, local_rank):
                 "api": "D3DP.ddim_sample_flip + Engine.jpma from pinned host tensors, aggregated poses copied back "
                        "into pinned host buffers"},
         "gpu_launches": launches_per_call * args.steps,
-        "launch_mode": "one CUDA graph per sampler call (%d kernel nodes) + 1 JPMA launch" % (launches_per_call - 1),
+        "launch_mode": "one CUDA graph per sampler call (%d kernel nodes) + the argument-block and JPMA launches" % (launches_per_call - 2),
         "phase_ms": phase_ms,
         "sampler_tflops": flops / t_total / 1e12 / world,
         "sampler_frac_of_sustained_peak": flops / t_total / 1e12 / world / peaks["tflops_sustained"],

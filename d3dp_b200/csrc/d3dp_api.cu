@@ -43,7 +43,7 @@ struct BlockW {
 
 }  // namespace
 
-// One instantiated CUDA graph of the whole K-step sampler loop (852 kernel nodes at depth 8, K = 10).  Everything that
+// One instantiated CUDA graph of the whole K-step sampler loop (842 kernel nodes at depth 8, K = 10).  Everything that
 // differs between two calls with the same key goes through the DynArgs block in the workspace, so the graph is
 // replayed as is; the key holds everything that is baked into kernel parameters.
 struct SamplerGraph {
@@ -338,7 +338,7 @@ struct Workspace {
   size_t bytes;
 };
 
-Workspace carve(const d3dp_handle* h, void* base, int B, int H, int n_streams) {
+Workspace carve(const d3dp_handle* h, void* base, int B, int H, int n_streams, int K = 1) {
   const size_t T = static_cast<size_t>(n_streams) * kJ * h->cfg.frames;
   uint8_t* p = static_cast<uint8_t*>(base);
   size_t off = 0;
@@ -353,9 +353,9 @@ Workspace carve(const d3dp_handle* h, void* base, int B, int H, int n_streams) {
   w.qkv16 = reinterpret_cast<__half*>(take(T * 1536 * 2));
   w.o16 = reinterpret_cast<__half*>(take(T * 512 * 2));
   w.den = reinterpret_cast<float*>(take(static_cast<size_t>(n_streams) * h->cfg.frames * kJ * 3 * 4));
-  w.tau = reinterpret_cast<float*>(take(static_cast<size_t>(B) * 512 * 4));
+  w.tau = reinterpret_cast<float*>(take(static_cast<size_t>(K) * B * 512 * 4));  // sampler: all K steps' embeddings
   w.img = reinterpret_cast<float*>(take(static_cast<size_t>(B) * H * h->cfg.frames * kJ * 3 * 4));
-  w.t = reinterpret_cast<long long*>(take(static_cast<size_t>(B) * 8));
+  w.t = reinterpret_cast<long long*>(take(static_cast<size_t>(K) * B * 8));
   w.dyn = reinterpret_cast<DynArgs*>(take(sizeof(DynArgs)));
   w.bytes = off;
   return w;
@@ -374,22 +374,27 @@ __global__ void fill_t_kernel(long long* t, int B, long long v) {
 // clamp_hi > 0 applies the sampler's clamp(+-1.1 scale)/scale on the fly (common/diffusionpose.py:136-137,148-149).
 int run_denoiser(d3dp_handle* h, const Workspace& w, const DynArgs* dyn, const float* x2d, const float* x2d_flip,
                  const float* img, const long long* t_dev, int B, int H, int n_streams, float clamp_hi,
-                 cudaStream_t st, const float* drop_scale = nullptr) {
+                 cudaStream_t st, const float* drop_scale = nullptr, const float* tau_ready = nullptr) {
   int rc;
   if ((rc = ensure_attrs(h))) return rc;
   const int F = h->cfg.frames, depth = h->cfg.depth;
   const int T = n_streams * kJ * F;
 
-  time_mlp_kernel<<<B, 512, 0, st>>>(t_dev, F32(h, "time_mlp.1.weight"), F32(h, "time_mlp.1.bias"),
-                                    F32(h, "time_mlp.3.weight"), F32(h, "time_mlp.3.bias"), w.tau);
-  CK(cudaGetLastError());
+  // timestep embedding of this forward: computed here, or (sampler) already in place for all K steps: `tau` then
+  // points at step k's [B,512] slice and t_dev is null
+  const float* tau = tau_ready ? tau_ready : w.tau;
+  if (!tau_ready) {
+    time_mlp_kernel<<<B, 512, 0, st>>>(t_dev, F32(h, "time_mlp.1.weight"), F32(h, "time_mlp.1.bias"),
+                                      F32(h, "time_mlp.3.weight"), F32(h, "time_mlp.3.bias"), w.tau);
+    CK(cudaGetLastError());
+  }
 
   EmbedParams ep;
   ep.dyn = dyn; ep.x2d = x2d; ep.x2d_flip = x2d_flip; ep.img = img;
   ep.w_e = F32(h, "Spatial_patch_to_embedding.weight");
   ep.b_e = F32(h, "Spatial_patch_to_embedding.bias");
   ep.spos = F32(h, "Spatial_pos_embed");
-  ep.tau = w.tau;
+  ep.tau = tau;
   ep.ln_g = static_cast<const float*>(h->sblk[0].n1w->dev);
   ep.ln_b = static_cast<const float*>(h->sblk[0].n1b->dev);
   ep.ln_eps = 1e-6f;
@@ -498,12 +503,21 @@ int sampler_body(d3dp_handle* h, const Workspace& w, int B, int H, int K, int fl
   // img ~ N(0, I)  (common/diffusionpose.py:225): injected, or Philox draw 0
   init_img_kernel<<<grid_for(n_img, h->num_sms), 256, 0, st>>>(w.img, w.dyn, B, H, per_bh, h_offset, H_total);
   CK(cudaGetLastError());
+  // the K timestep embeddings (time-MLP of a [B] vector: 4 CTAs of work each) in ONE launch ahead of the loop instead
+  // of K launches on its critical path
+  for (int k = 0; k < K; ++k) {
+    fill_t_kernel<<<(B + 127) / 128, 128, 0, st>>>(w.t + static_cast<size_t>(k) * B, B, static_cast<long long>(times[k]));
+    CK(cudaGetLastError());
+  }
+  time_mlp_kernel<<<K * B, 512, 0, st>>>(w.t, F32(h, "time_mlp.1.weight"), F32(h, "time_mlp.1.bias"),
+                                        F32(h, "time_mlp.3.weight"), F32(h, "time_mlp.3.bias"), w.tau);
+  CK(cudaGetLastError());
   const float scale = h->cfg.scale;
   for (int k = 0; k < K; ++k) {
     const int t = times[k], t_next = times[k + 1];
-    fill_t_kernel<<<(B + 127) / 128, 128, 0, st>>>(w.t, B, static_cast<long long>(t));
-    CK(cudaGetLastError());
-    if ((rc = run_denoiser(h, w, w.dyn, nullptr, nullptr, w.img, w.t, B, H, n_streams, 1.1f * scale, st))) return rc;
+    if ((rc = run_denoiser(h, w, w.dyn, nullptr, nullptr, w.img, nullptr, B, H, n_streams, 1.1f * scale, st, nullptr,
+                           w.tau + static_cast<size_t>(k) * B * 512)))
+      return rc;
     DdimParams dp{};
     dp.den = w.den; dp.img = w.img; dp.dyn = w.dyn;
     dp.B = B; dp.H = H; dp.K = K; dp.F = F; dp.k = k;
@@ -693,7 +707,7 @@ int d3dp_time_list(int32_t num_timesteps, int32_t K, int32_t* out) {
 int d3dp_workspace_bytes(const d3dp_handle* h, int32_t B, int32_t H, int32_t flip, size_t* bytes) {
   if (!h || !bytes || B < 1 || H < 1) return D3DP_E_INVALID;
   const int n_streams = B * H * (flip ? 2 : 1);
-  *bytes = carve(h, nullptr, B, H, n_streams).bytes;
+  *bytes = carve(h, nullptr, B, H, n_streams, h->cfg.num_timesteps).bytes;  // room for any K <= num_timesteps
   return D3DP_OK;
 }
 
@@ -725,7 +739,7 @@ int d3dp_ddim_sample(d3dp_handle* h, const float* x2d, const float* x2d_flip, co
   if ((rc = ensure_attrs(h))) return rc;
   const int flip = x2d_flip ? 1 : 0;
   const int n_streams = B * H * (flip ? 2 : 1);
-  Workspace w = carve(h, workspace, B, H, n_streams);
+  Workspace w = carve(h, workspace, B, H, n_streams, h->cfg.num_timesteps);  // layout independent of K
   if (w.bytes > workspace_bytes) return fail(h, D3DP_E_WORKSPACE, "ddim_sample: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
