@@ -50,16 +50,27 @@ __global__ void __launch_bounds__(256) attn_spatial_kernel(const AttnSParams p) 
   const int g = lane >> 2, t = lane & 3;
   const int num_items = p.num_streams * p.F;
 
-  // gather the 17 qkv rows of one (stream, frame) into buffer `buf`: row(j) = (s*17 + j)*F + f
+  // gather the 17 qkv rows of one (stream, frame) into buffer `buf`: row(j) = (s*17 + j)*F + f.  A thread copies the
+  // same 13 (joint, 16-byte piece) slots of every item: their source / destination offsets are computed once, so a
+  // copy costs an add and the cp.async instead of two divisions and 64-bit address arithmetic
+  constexpr int SP_COPIES = (SP_J * 192 + 255) / 256;  // 16-byte pieces per thread and item (256 threads)
+  uint32_t src_off[SP_COPIES], dst_off[SP_COPIES];     // in halfs / bytes; src relative to the item's (s, j=0, f) row
+#pragma unroll
+  for (int i = 0; i < SP_COPIES; ++i) {
+    const int idx = threadIdx.x + i * 256;
+    const int j = idx / 192, ch = idx % 192;  // 192 x 16 B per row
+    src_off[i] = static_cast<uint32_t>(j) * static_cast<uint32_t>(p.F) * 1536u + ch * 8;
+    dst_off[i] = (j * SP_ROW_HALFS + ch * 8) * 2;
+  }
   auto prefetch = [&](int item, int buf) {
     const int s = item / p.F, f = item % p.F;
-    __half* dstb = sm + buf * (SP_BUF_BYTES / 2);
-    for (int idx = threadIdx.x; idx < SP_J * 192; idx += blockDim.x) {
-      const int j = idx / 192, ch = idx % 192;  // 192 x 16 B per row
-      const __half* src = p.qkv + (static_cast<size_t>(s * SP_J + j) * p.F + f) * 1536 + ch * 8;
-      const uint32_t dst = smem_u32(dstb + j * SP_ROW_HALFS + ch * 8);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-    }
+    const __half* srcb = p.qkv + (static_cast<size_t>(s) * SP_J * p.F + f) * 1536;
+    const uint32_t dstb = smem_u32(sm + buf * (SP_BUF_BYTES / 2));
+#pragma unroll
+    for (int i = 0; i < SP_COPIES; ++i)
+      if (i + 1 < SP_COPIES || threadIdx.x + i * 256 < SP_J * 192)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstb + dst_off[i]), "l"(srcb + src_off[i])
+                     : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   if (threadIdx.x < 4) reinterpret_cast<uint32_t*>(sp_smem + SP_ZERO_OFFSET)[threadIdx.x] = 0u;
